@@ -1,0 +1,415 @@
+// Register-tiled fused cell kernel for Cartesian cells (the fast path).
+//
+// Work decomposition: n = k+1 threads per cell, 32/n cells per warp, one warp
+// per batch of cells; a warp never synchronises with another warp.  Each
+// thread owns one n x n plane of the cell's n^3 values in registers:
+//
+//   P1 (thread = z, plane (x,y)):  gather -> hanging-node interpolation
+//        (x, y passes in registers, z pass by warp shuffles) ->
+//        a = M_y M_x u,  b = (M_y K_x + K_y M_x) u          -> shared memory
+//   P2 (thread = x, plane (y,z)):  r = h (M_z b + K_z a)      -> shared memory
+//   P3 (thread = z, plane (x,y)):  interpolation^T -> atomic scatter-add
+//
+// On a Cartesian cell the Laplace cell matrix produced by the reference's
+// evaluate / submit_gradient / integrate sequence with QGauss(k+1)
+// (benchmark_03.h:305-312) is exactly h (K x M x M + M x K x M + M x M x K) with
+// the 1D Gauss-integrated mass M and stiffness K; applying it in this form
+// needs 7 one-dimensional sweeps instead of 12 and no quadrature-point data.
+// M and K are persymmetric, so every sweep uses the even-odd decomposition.
+//
+// The DoF indices are stored warp-interleaved ([batch][plane slot][lane]) so
+// that every index load is one coalesced 128-byte request.
+#pragma once
+#include "kernels_generic.cuh"
+#include "shape_tables.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+
+namespace mfhn
+{
+constexpr int round_up_mod(int v, int r, int mod)
+{
+  while (v % mod != r % mod) ++v;
+  return v;
+}
+
+template <int n, typename Number>
+struct PlaneCfg
+{
+  static constexpr int cpw   = 32 / n;     // cells per warp
+  static constexpr int lanes = cpw * n;    // active lanes
+  static constexpr int mod   = sizeof(Number) == 8 ? 16 : 32;
+  // plane / cell strides chosen so that lane (cell c, thread t) hits bank
+  // (c n + t) mod `mod` in every phase: conflict-free shared memory traffic
+  static constexpr int ps    = round_up_mod(n * n, 1, mod);
+  static constexpr int cs    = round_up_mod(n * ps, n, mod);
+  static constexpr int warps = 4;
+  static constexpr int smem_per_warp = 2 * cpw * cs * (int)sizeof(Number);
+  static constexpr int smem  = warps * smem_per_warp;
+};
+
+constexpr bool plane_supported(int n) { return n >= 2 && n <= 6; }
+
+struct PlaneParams
+{
+  const uint32_t *pidx; // [n_batches][n*n][32]
+  const uint8_t *masks; // [n_cells]
+  const void *h;        // Number[n_cells]
+  const void *w0;       // Number[n*n] subface interpolation matrix (global copy)
+  const void *src;
+  void *dst;
+  long long cell_begin, cell_end, batch_begin, batch_end;
+  int apply_constraints;
+};
+
+// ---- even-odd application of a persymmetric matrix --------------------------
+template <int n, typename Number>
+__device__ __forceinline__ void eo_split(const Number (&x)[n], Number (&xs)[(n + 1) / 2], Number (&xd)[(n + 1) / 2])
+{
+  constexpr int h = n / 2;
+#pragma unroll
+  for (int j = 0; j < h; ++j)
+    {
+      xs[j] = x[j] + x[n - 1 - j];
+      xd[j] = x[j] - x[n - 1 - j];
+    }
+  if (n % 2)
+    {
+      xs[h] = x[h];
+      xd[h] = Number(0);
+    }
+}
+template <int n, int TE, int TO, bool INIT, typename Number>
+__device__ __forceinline__ void eo_mac(const Number (&xs)[(n + 1) / 2], const Number (&xd)[(n + 1) / 2],
+                                       Number (&se)[(n + 1) / 2], Number (&so)[(n + 1) / 2])
+{
+  constexpr int h = n / 2, he = (n + 1) / 2;
+#pragma unroll
+  for (int i = 0; i < he; ++i)
+#pragma unroll
+    for (int j = 0; j < he; ++j)
+      {
+        const Number c = Shape<Number>::template eo<n, TE>(i * he + j);
+        se[i]          = (INIT && j == 0) ? c * xs[j] : se[i] + c * xs[j];
+      }
+#pragma unroll
+  for (int i = 0; i < h; ++i)
+#pragma unroll
+    for (int j = 0; j < h; ++j)
+      {
+        const Number c = Shape<Number>::template eo<n, TO>(i * he + j);
+        so[i]          = (INIT && j == 0) ? c * xd[j] : so[i] + c * xd[j];
+      }
+}
+template <int n, typename Number>
+__device__ __forceinline__ void eo_merge(const Number (&se)[(n + 1) / 2], const Number (&so)[(n + 1) / 2], Number (&y)[n])
+{
+  constexpr int h = n / 2;
+#pragma unroll
+  for (int i = 0; i < h; ++i)
+    {
+      y[i]         = se[i] + so[i];
+      y[n - 1 - i] = se[i] - so[i];
+    }
+  if (n % 2) y[h] = se[h];
+}
+
+// p = M x, q = K x
+template <int n, typename Number>
+__device__ __forceinline__ void apply_MK(const Number (&x)[n], Number (&p)[n], Number (&q)[n])
+{
+  if (n >= 4)
+    {
+      Number xs[(n + 1) / 2], xd[(n + 1) / 2], se[(n + 1) / 2], so[(n + 1) / 2];
+      eo_split<n>(x, xs, xd);
+      eo_mac<n, T_ME, T_MO, true>(xs, xd, se, so);
+      eo_merge<n>(se, so, p);
+      eo_mac<n, T_KE, T_KO, true>(xs, xd, se, so);
+      eo_merge<n>(se, so, q);
+    }
+  else
+    {
+      mat_vec<n, T_M, false>(x, p);
+      mat_vec<n, T_K, false>(x, q);
+    }
+}
+// a = M p, b = M q + K p
+template <int n, typename Number>
+__device__ __forceinline__ void apply_M_MK(const Number (&p)[n], const Number (&q)[n], Number (&a)[n], Number (&b)[n])
+{
+  if (n >= 4)
+    {
+      constexpr int he = (n + 1) / 2;
+      Number ps[he], pd[he], qs[he], qd[he], se[he], so[he];
+      eo_split<n>(p, ps, pd);
+      eo_split<n>(q, qs, qd);
+      eo_mac<n, T_ME, T_MO, true>(ps, pd, se, so);
+      eo_merge<n>(se, so, a);
+      eo_mac<n, T_ME, T_MO, true>(qs, qd, se, so);
+      eo_mac<n, T_KE, T_KO, false>(ps, pd, se, so);
+      eo_merge<n>(se, so, b);
+    }
+  else
+    {
+      Number t[n];
+      mat_vec<n, T_M, false>(p, a);
+      mat_vec<n, T_M, false>(q, b);
+      mat_vec<n, T_K, false>(p, t);
+#pragma unroll
+      for (int i = 0; i < n; ++i) b[i] += t[i];
+    }
+}
+// r = M b + K a
+template <int n, typename Number>
+__device__ __forceinline__ void apply_Mb_Ka(const Number (&a)[n], const Number (&b)[n], Number (&r)[n])
+{
+  if (n >= 4)
+    {
+      constexpr int he = (n + 1) / 2;
+      Number as[he], ad[he], bs[he], bd[he], se[he], so[he];
+      eo_split<n>(a, as, ad);
+      eo_split<n>(b, bs, bd);
+      eo_mac<n, T_ME, T_MO, true>(bs, bd, se, so);
+      eo_mac<n, T_KE, T_KO, false>(as, ad, se, so);
+      eo_merge<n>(se, so, r);
+    }
+  else
+    {
+      Number t[n];
+      mat_vec<n, T_M, false>(b, r);
+      mat_vec<n, T_K, false>(a, t);
+#pragma unroll
+      for (int i = 0; i < n; ++i) r[i] += t[i];
+    }
+}
+
+// ---- hanging-node interpolation on thread-owned (x,y) planes ----------------
+// u[y][x] is the plane z = t of the cell; the n threads of a cell sit in lanes
+// base .. base+n-1.  x and y passes stay in registers, the z pass exchanges the
+// ring values (x or y on the cell boundary) with warp shuffles.
+template <int n, bool transpose, typename Number>
+__device__ __forceinline__ void hn_plane(Number (&u)[n][n], unsigned mask, int t, int base, const Number *__restrict__ w0)
+{
+  constexpr int k = n - 1;
+  unsigned face, edge, cb;
+  decode_mask(mask, face, edge, cb);
+  const bool fx = face & 1u, fy = face & 2u, fz = face & 4u;
+  const bool ex = edge & 1u, ey = edge & 2u, ez = edge & 4u;
+  const bool upx = cb & 1u, upy = cb & 2u, upz = cb & 4u;
+  const int X0 = upx ? k : 0, Y0 = upy ? k : 0, Z0 = upz ? k : 0;
+  const bool onz = (t == Z0);
+  const bool planez = fz && onz; // the whole plane lies on the constrained z face
+  // pass x: lines along x, one per y
+#pragma unroll
+  for (int y = 0; y < n; ++y)
+    {
+      const bool sel = planez || ((y == Y0) && (fy || (ex && onz)));
+      if (sel)
+        {
+          Number v[n], w[n];
+#pragma unroll
+          for (int i = 0; i < n; ++i) v[i] = upx ? u[y][k - i] : u[y][i];
+          mat_vec<n, T_W0, transpose>(v, w);
+#pragma unroll
+          for (int i = 0; i < n; ++i)
+            {
+              u[y][i] = upx ? w[k - i] : w[i];
+            }
+        }
+    }
+  // pass y: lines along y, one per x
+#pragma unroll
+  for (int x = 0; x < n; ++x)
+    {
+      const bool sel = planez || ((x == X0) && (fx || (ey && onz)));
+      if (sel)
+        {
+          Number v[n], w[n];
+#pragma unroll
+          for (int i = 0; i < n; ++i) v[i] = upy ? u[k - i][x] : u[i][x];
+          mat_vec<n, T_W0, transpose>(v, w);
+#pragma unroll
+          for (int i = 0; i < n; ++i) u[i][x] = upy ? w[k - i] : w[i];
+        }
+    }
+  // pass z: lines along z through ring positions, exchanged by shuffles
+  Number wz[n];
+#pragma unroll
+  for (int zz = 0; zz < n; ++zz)
+    {
+      // forward: W_bz[t][zz];  transpose: W_bz[zz][t];  W_1[i][j] = W_0[k-i][k-j]
+      const int i = transpose ? zz : t, j = transpose ? t : zz;
+      wz[zz]      = w0[upz ? (k - i) * n + (k - j) : i * n + j];
+    }
+#pragma unroll
+  for (int y = 0; y < n; ++y)
+#pragma unroll
+    for (int x = 0; x < n; ++x)
+      {
+        if (!(x == 0 || x == k || y == 0 || y == k)) continue;
+        const bool sel = ((x == X0) && fx) || ((y == Y0) && fy) || (ez && x == X0 && y == Y0);
+        if (__any_sync(0xffffffffu, sel))
+          {
+            Number acc = Number(0);
+#pragma unroll
+            for (int zz = 0; zz < n; ++zz) acc += wz[zz] * __shfl_sync(0xffffffffu, u[y][x], base + zz);
+            if (sel) u[y][x] = acc;
+          }
+      }
+}
+
+template <int n, typename Number>
+__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32) plane_cell_kernel(const PlaneParams p)
+{
+  using Cfg = PlaneCfg<n, Number>;
+  constexpr int ps = Cfg::ps, cs = Cfg::cs;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long batch = p.batch_begin + (long long)blockIdx.x * Cfg::warps + warp;
+  if (batch >= p.batch_end) return; // warps are independent: no block-level barrier below
+  Number *A = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * 2 * Cfg::cpw * cs;
+  Number *B = A + Cfg::cpw * cs;
+
+  const int c = lane / n, t = lane - c * n;
+  const bool active = lane < Cfg::lanes;
+  const long long cell = batch * Cfg::cpw + c;
+  const bool valid = active && cell >= p.cell_begin && cell < p.cell_end;
+  const Number *__restrict__ src = static_cast<const Number *>(p.src);
+  Number *__restrict__ dst = static_cast<Number *>(p.dst);
+
+  // ---- P1: gather ------------------------------------------------------------
+  uint32_t idx[n * n];
+  {
+    const uint32_t *ip = p.pidx + batch * (long long)(n * n * 32) + lane;
+#pragma unroll
+    for (int j = 0; j < n * n; ++j) idx[j] = valid ? __ldg(ip + j * 32) : 0xffffffffu;
+  }
+  Number u[n][n];
+#pragma unroll
+  for (int j = 0; j < n * n; ++j) u[j / n][j % n] = (idx[j] != 0xffffffffu) ? __ldg(src + idx[j]) : Number(0);
+  const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
+  const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
+  const bool any_hn   = __any_sync(0xffffffffu, mask != 0u);
+  if (any_hn) hn_plane<n, false>(u, mask, t, lane - t, static_cast<const Number *>(p.w0));
+
+  // ---- P1: x and y sweeps ------------------------------------------------------
+  {
+    Number pp[n][n], qq[n][n];
+#pragma unroll
+    for (int y = 0; y < n; ++y) apply_MK<n>(u[y], pp[y], qq[y]);
+#pragma unroll
+    for (int x = 0; x < n; ++x)
+      {
+        Number pc[n], qc[n], a[n], b[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+          {
+            pc[i] = pp[i][x];
+            qc[i] = qq[i][x];
+          }
+        apply_M_MK<n>(pc, qc, a, b);
+        if (active)
+          {
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              {
+                A[c * cs + t * ps + i * n + x] = a[i];
+                B[c * cs + t * ps + i * n + x] = b[i];
+              }
+          }
+      }
+  }
+  __syncwarp();
+  // ---- P2: z sweep (thread = x) ----------------------------------------------
+  if (active)
+    {
+#pragma unroll
+      for (int y = 0; y < n; ++y)
+        {
+          Number a[n], b[n], r[n];
+#pragma unroll
+          for (int z = 0; z < n; ++z)
+            {
+              a[z] = A[c * cs + z * ps + y * n + t];
+              b[z] = B[c * cs + z * ps + y * n + t];
+            }
+          apply_Mb_Ka<n>(a, b, r);
+#pragma unroll
+          for (int z = 0; z < n; ++z) A[c * cs + z * ps + y * n + t] = h * r[z];
+        }
+    }
+  __syncwarp();
+  // ---- P3: interpolation^T and scatter (thread = z) --------------------------
+  if (active)
+    {
+#pragma unroll
+      for (int j = 0; j < n * n; ++j) u[j / n][j % n] = A[c * cs + t * ps + j];
+    }
+  if (any_hn) hn_plane<n, true>(u, mask, t, lane - t, static_cast<const Number *>(p.w0));
+#pragma unroll
+  for (int j = 0; j < n * n; ++j)
+    if (idx[j] != 0xffffffffu) atomicAdd(dst + idx[j], u[j / n][j % n]);
+}
+
+// ---- host side ------------------------------------------------------------------
+struct PlaneLayout
+{
+  int n = 0;
+  long long n_cells = 0, n_batches = 0;
+  uint32_t *d_pidx = nullptr;
+  void *d_w0       = nullptr;
+
+  void free()
+  {
+    cudaFree(d_pidx);
+    cudaFree(d_w0);
+    d_pidx = nullptr;
+    d_w0   = nullptr;
+  }
+  void build(int n_, int number, long long n_cells_, const uint32_t *idx, const double *w0);
+};
+
+template <int n, typename Number>
+void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream)
+{
+  using Cfg = PlaneCfg<n, Number>;
+  static bool attr[64] = {};
+  if (!attr[device])
+    {
+      cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+      attr[device] = true;
+    }
+  PlaneParams p;
+  p.pidx              = L.d_pidx;
+  p.masks             = cp.masks;
+  p.h                 = cp.geom;
+  p.w0                = L.d_w0;
+  p.src               = cp.src;
+  p.dst               = cp.dst;
+  p.cell_begin        = cp.cell_begin;
+  p.cell_end          = cp.cell_end;
+  p.batch_begin       = cp.cell_begin / Cfg::cpw;
+  p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
+  p.apply_constraints = cp.apply_constraints;
+  const long long nb  = p.batch_end - p.batch_begin;
+  if (nb <= 0) return;
+  const unsigned grid = (unsigned)((nb + Cfg::warps - 1) / Cfg::warps);
+  plane_cell_kernel<n, Number><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("plane kernel launch: ") + cudaGetErrorString(e));
+}
+
+template <int n, typename Number>
+void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream)
+{
+  if constexpr (plane_supported(n))
+    launch_plane_impl<n, Number>(L, cp, device, stream);
+  else
+    throw std::runtime_error("plane kernel not available for this degree");
+}
+} // namespace mfhn

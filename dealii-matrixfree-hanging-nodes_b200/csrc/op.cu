@@ -1,0 +1,549 @@
+// Operator object behind the C ABI: device-resident MatrixFree data + kernel
+// dispatch.  Stands in for CUDAWrappers::MatrixFree::reinit / cell_loop as used
+// by LaplaceOperator<..., MemorySpace::CUDA> (benchmark_03.h:319-357).
+#include "../../include/mfhn.h"
+#include "error.hpp"
+#include "fe1d.hpp"
+#include "kernels_generic.cuh"
+#include "kernels_plane.cuh"
+#include "octree.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace mfhn
+{
+
+#define CUDA_CHECK(x)                                                                            \
+  do                                                                                             \
+    {                                                                                            \
+      cudaError_t e_ = (x);                                                                      \
+      if (e_ != cudaSuccess)                                                                     \
+        throw CudaError(std::string(#x) + ": " + cudaGetErrorString(e_));                        \
+    }                                                                                            \
+  while (0)
+
+namespace
+{
+std::mutex g_table_mutex;
+bool g_tables_uploaded[64] = {};
+
+void upload_tables(int device)
+{
+  std::lock_guard<std::mutex> lock(g_table_mutex);
+  if (device >= 0 && device < 64 && g_tables_uploaded[device]) return;
+  static ShapeTables<double> hd;
+  static ShapeTables<float> hf;
+  std::memset(&hd, 0, sizeof(hd));
+  for (int k = 1; k <= 8; ++k)
+    {
+      const Shape1D s = make_shape(k);
+      const int n = k + 1, h = n / 2, he = (n + 1) / 2;
+      auto &t = hd.full[k - 1];
+      for (int i = 0; i < n * n; ++i)
+        {
+          t[T_S][i]  = s.S[i];
+          t[T_DC][i] = s.Dc[i];
+          t[T_W0][i] = s.W[0][i];
+          t[T_M][i]  = s.M[i];
+          t[T_K][i]  = s.K[i];
+        }
+      for (int i = 0; i < n; ++i) hd.qw[k - 1][i] = s.qw[i];
+      // even-odd halves of the persymmetric M and K: E = (A[i][j] + A[i][n-1-j]) / 2 (middle
+      // column: A[i][m]), O = (A[i][j] - A[i][n-1-j]) / 2
+      if (he <= MAX_HE)
+        for (int which = 0; which < 2; ++which)
+          {
+            const std::vector<double> &A = which == 0 ? s.M : s.K;
+            double *E = hd.eo[k - 1][which == 0 ? T_ME : T_KE], *O = hd.eo[k - 1][which == 0 ? T_MO : T_KO];
+            for (int i = 0; i < he; ++i)
+              for (int j = 0; j < he; ++j)
+                {
+                  if (j < h)
+                    {
+                      E[i * he + j] = 0.5 * (A[i * n + j] + A[i * n + (n - 1 - j)]);
+                      O[i * he + j] = 0.5 * (A[i * n + j] - A[i * n + (n - 1 - j)]);
+                    }
+                  else
+                    {
+                      E[i * he + j] = A[i * n + j];
+                      O[i * he + j] = 0;
+                    }
+                }
+          }
+    }
+  {
+    const double *ps = reinterpret_cast<const double *>(&hd);
+    float *pf        = reinterpret_cast<float *>(&hf);
+    for (size_t i = 0; i < sizeof(hd) / sizeof(double); ++i) pf[i] = (float)ps[i];
+  }
+  CUDA_CHECK(cudaMemcpyToSymbol(c_shape_d, &hd, sizeof(hd)));
+  CUDA_CHECK(cudaMemcpyToSymbol(c_shape_f, &hf, sizeof(hf)));
+  if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
+}
+
+template <typename T>
+T *to_device(const std::vector<T> &h)
+{
+  T *d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+} // namespace
+
+void PlaneLayout::build(int n_, int number, long long n_cells_, const uint32_t *idx, const double *w0)
+{
+  n               = n_;
+  n_cells         = n_cells_;
+  const int cpw   = 32 / n;
+  n_batches       = (n_cells + cpw - 1) / cpw;
+  const int n2    = n * n;
+  const long long n3 = (long long)n2 * n;
+  std::vector<uint32_t> p((size_t)std::max<long long>(n_batches, 1) * n2 * 32, 0xffffffffu);
+#pragma omp parallel for schedule(static)
+  for (long long c = 0; c < n_cells; ++c)
+    {
+      const long long batch = c / cpw;
+      const int slot        = (int)(c % cpw);
+      for (int t = 0; t < n; ++t)
+        for (int j = 0; j < n2; ++j) p[((size_t)batch * n2 + j) * 32 + slot * n + t] = idx[c * n3 + j + (long long)n2 * t];
+    }
+  d_pidx = to_device(p);
+  if (number == MFHN_F64)
+    {
+      std::vector<double> w(w0, w0 + n2);
+      d_w0 = to_device(w);
+    }
+  else
+    {
+      std::vector<float> w(w0, w0 + n2);
+      d_w0 = to_device(w);
+    }
+}
+
+struct Operator
+{
+  int degree = 0, number = 0, device = 0, geometry_type = 0;
+  int apply_constraints = 1, kernel = MFHN_KERNEL_AUTO;
+  long long n_cells = 0, n_owned = 0, n_ghost = 0, n_cells_hn = 0;
+  uint32_t *d_idx = nullptr;    // reference layout [cell][lexicographic]
+  uint8_t *d_masks = nullptr;
+  void *d_geom = nullptr;       // Number h[cell] or Number G[cell][6]
+  PlaneLayout plane;            // warp-interleaved layout of the register-tiled kernel
+  long long launches = 0;
+
+  ~Operator()
+  {
+    cudaFree(d_idx);
+    cudaFree(d_masks);
+    cudaFree(d_geom);
+    plane.free();
+  }
+};
+
+// ---------------------------------------------------------------------------
+template <int n, typename Number, int V>
+void launch_generic(const Operator &op, const CellLoopParams &p, cudaStream_t stream)
+{
+  using Cfg           = GenericCfg<n>;
+  const size_t smem   = (size_t)Cfg::cpb * generic_n_arrays<V>() * Cfg::cs * sizeof(Number);
+  static bool attr[64] = {};
+  if (smem > 48 * 1024 && !attr[op.device])
+    {
+      CUDA_CHECK(cudaFuncSetAttribute(generic_cell_kernel<n, Number, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[op.device] = true;
+    }
+  const long long nc = p.cell_end - p.cell_begin;
+  if (nc <= 0) return;
+  const unsigned grid = (unsigned)((nc + Cfg::cpb - 1) / Cfg::cpb);
+  generic_cell_kernel<n, Number, V><<<grid, Cfg::threads, smem, stream>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int n, typename Number>
+void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
+{
+  if (kernel == MFHN_KERNEL_PLANE)
+    {
+      launch_plane<n, Number>(op.plane, p, op.device, stream);
+    }
+  else if (op.geometry_type == MFHN_GEOM_AFFINE)
+    launch_generic<n, Number, GV_QPOINT_METRIC>(op, p, stream);
+  else if (kernel == MFHN_KERNEL_SEPARABLE)
+    launch_generic<n, Number, GV_SEPARABLE>(op, p, stream);
+  else
+    launch_generic<n, Number, GV_QPOINT_CARTESIAN>(op, p, stream);
+  ++op.launches;
+}
+
+template <typename Number>
+void launch_number(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
+{
+  switch (op.degree)
+    {
+      case 1: launch_n<2, Number>(op, kernel, p, stream); break;
+      case 2: launch_n<3, Number>(op, kernel, p, stream); break;
+      case 3: launch_n<4, Number>(op, kernel, p, stream); break;
+      case 4: launch_n<5, Number>(op, kernel, p, stream); break;
+      case 5: launch_n<6, Number>(op, kernel, p, stream); break;
+      case 6: launch_n<7, Number>(op, kernel, p, stream); break;
+      case 7: launch_n<8, Number>(op, kernel, p, stream); break;
+      case 8: launch_n<9, Number>(op, kernel, p, stream); break;
+      default: throw InvalidArgument("unsupported degree");
+    }
+}
+
+int resolve_kernel(const Operator &op)
+{
+  int kernel = op.kernel;
+  if (kernel == MFHN_KERNEL_AUTO)
+    kernel = (op.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(op.degree + 1)) ? MFHN_KERNEL_PLANE :
+             (op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_SEPARABLE : MFHN_KERNEL_QPOINT);
+  if (op.geometry_type == MFHN_GEOM_AFFINE && kernel != MFHN_KERNEL_QPOINT)
+    throw InvalidArgument("affine geometry requires MFHN_KERNEL_QPOINT");
+  if (kernel == MFHN_KERNEL_PLANE && !plane_supported(op.degree + 1))
+    throw NotImplemented("MFHN_KERNEL_PLANE is not available for this degree");
+  return kernel;
+}
+
+void op_vmult_range(Operator &op, void *dst, const void *src, cudaStream_t stream, long long cb, long long ce)
+{
+  if (ce < 0) ce = op.n_cells;
+  if (cb < 0 || ce > op.n_cells || cb > ce) throw InvalidArgument("cell range out of bounds");
+  CellLoopParams p;
+  p.idx               = op.d_idx;
+  p.masks             = op.d_masks;
+  p.geom              = op.d_geom;
+  p.src               = src;
+  p.dst               = dst;
+  p.cell_begin        = cb;
+  p.cell_end          = ce;
+  p.apply_constraints = op.apply_constraints;
+  const int kernel    = resolve_kernel(op);
+  if (op.number == MFHN_F64)
+    launch_number<double>(op, kernel, p, stream);
+  else
+    launch_number<float>(op, kernel, p, stream);
+}
+
+Operator *op_create(const mfhn_op_desc &d)
+{
+  if (d.degree < 1 || d.degree > 8) throw InvalidArgument("degree must be in 1..8");
+  if (d.number != MFHN_F64 && d.number != MFHN_F32) throw InvalidArgument("number must be MFHN_F64 or MFHN_F32");
+  if (d.n_cells < 0 || d.n_owned < 0 || d.n_ghost < 0) throw InvalidArgument("negative size");
+  if (d.n_cells > 0 && (!d.dof_indices || !d.masks || !d.geometry)) throw InvalidArgument("null array");
+  if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE) throw InvalidArgument("unknown geometry type");
+  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_PLANE) throw InvalidArgument("unknown kernel");
+  int device = d.device;
+  if (device < 0)
+    CUDA_CHECK(cudaGetDevice(&device));
+  else
+    CUDA_CHECK(cudaSetDevice(device));
+  upload_tables(device);
+  std::unique_ptr<Operator> op(new Operator);
+  op->degree            = d.degree;
+  op->number            = d.number;
+  op->device            = device;
+  op->geometry_type     = d.geometry_type;
+  op->apply_constraints = d.apply_constraints;
+  op->kernel            = d.kernel;
+  op->n_cells           = d.n_cells;
+  op->n_owned           = d.n_owned;
+  op->n_ghost           = d.n_ghost;
+  const int n           = d.degree + 1;
+  const long long n3    = (long long)n * n * n;
+  const long long nvec  = d.n_owned + d.n_ghost;
+  for (long long i = 0; i < d.n_cells * n3; ++i)
+    if (d.dof_indices[i] >= (unsigned long long)nvec) throw InvalidArgument("dof index out of range");
+  for (long long c = 0; c < d.n_cells; ++c)
+    {
+      if (!check_kind(decompress_kind(d.masks[c])) || compress_kind(decompress_kind(d.masks[c])) != d.masks[c])
+        throw InvalidArgument("invalid compressed constraint mask");
+      op->n_cells_hn += d.masks[c] != 0;
+    }
+  CUDA_CHECK(cudaMalloc(&op->d_idx, std::max<size_t>(1, d.n_cells * n3) * sizeof(uint32_t)));
+  CUDA_CHECK(cudaMemcpy(op->d_idx, d.dof_indices, d.n_cells * n3 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMalloc(&op->d_masks, std::max<size_t>(1, d.n_cells)));
+  CUDA_CHECK(cudaMemcpy(op->d_masks, d.masks, d.n_cells, cudaMemcpyHostToDevice));
+  // geometry -> per-cell factors in the operator's Number type
+  std::vector<double> g;
+  if (d.geometry_type == MFHN_GEOM_CARTESIAN)
+    g.assign(d.geometry, d.geometry + d.n_cells);
+  else
+    {
+      g.resize(d.n_cells * 6);
+      for (long long c = 0; c < d.n_cells; ++c)
+        {
+          const double *J = d.geometry + 9 * c;
+          const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+          if (!(det > 0)) throw InvalidArgument("non-positive Jacobian determinant");
+          double inv[9] = {(J[4] * J[8] - J[5] * J[7]) / det, (J[2] * J[7] - J[1] * J[8]) / det, (J[1] * J[5] - J[2] * J[4]) / det,
+                           (J[5] * J[6] - J[3] * J[8]) / det, (J[0] * J[8] - J[2] * J[6]) / det, (J[2] * J[3] - J[0] * J[5]) / det,
+                           (J[3] * J[7] - J[4] * J[6]) / det, (J[1] * J[6] - J[0] * J[7]) / det, (J[0] * J[4] - J[1] * J[3]) / det};
+          // G = det * inv * inv^T  (symmetric): rows of inv are gradients of xi_r
+          int t = 0;
+          for (int r = 0; r < 3; ++r)
+            for (int s = r; s < 3; ++s)
+              g[6 * c + t++] = det * (inv[3 * r] * inv[3 * s] + inv[3 * r + 1] * inv[3 * s + 1] + inv[3 * r + 2] * inv[3 * s + 2]);
+        }
+    }
+  if (d.number == MFHN_F64)
+    op->d_geom = to_device(g);
+  else
+    {
+      std::vector<float> gf(g.begin(), g.end());
+      op->d_geom = to_device(gf);
+    }
+  if (d.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(n))
+    {
+      const Shape1D sh = make_shape(d.degree);
+      op->plane.build(n, d.number, d.n_cells, d.dof_indices, sh.W[0].data());
+    }
+  resolve_kernel(*op);
+  return op.release();
+}
+
+// ---------------------------------------------------------------------------
+// auxiliary kernels
+template <typename Number>
+__global__ void pack_kernel(Number *buf, const Number *vec, const int32_t *idx, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = vec[idx[i]];
+}
+template <typename Number>
+__global__ void unpack_add_kernel(Number *vec, const Number *buf, const int32_t *idx, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vec[idx[i]] += buf[i];
+}
+
+template <int n, typename Number>
+__global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n_cells, int transpose)
+{
+  // FEEvaluationHangingNodesFactory::apply on cell-local values (benchmark_00_likwid.cc:56-59)
+  __shared__ Number s[n * n * n];
+  const long long cell = blockIdx.x;
+  const int l = threadIdx.x, a = l % n, b = l / n;
+  Number *g = values + cell * (n * n * n);
+  for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
+  unsigned face, edge, cb;
+  const unsigned mask = masks[cell];
+  decode_mask(mask, face, edge, cb);
+  __syncthreads();
+  for (int d = 0; d < 3; ++d)
+    {
+      Number *line   = s + (d == 0 ? n * (a + n * b) : d == 1 ? a + n * n * b : a + n * b);
+      const int strd = d == 0 ? 1 : d == 1 ? n : n * n;
+      if (mask)
+        {
+          if (transpose)
+            hn_pass_line<n, true>(line, strd, d, a, b, face, edge, cb);
+          else
+            hn_pass_line<n, false>(line, strd, d, a, b, face, edge, cb);
+        }
+      __syncthreads();
+    }
+  for (int z = 0; z < n; ++z) g[l + n * n * z] = s[l + n * n * z];
+}
+
+template <typename Number>
+void hn_only(Operator &op, void *values, int transpose, cudaStream_t st)
+{
+  if (op.n_cells == 0) return;
+  const unsigned grid = (unsigned)op.n_cells;
+#define HN_CASE(N)                                                                                            \
+  case N - 1:                                                                                                 \
+    hn_only_kernel<N, Number><<<grid, N * N, 0, st>>>((Number *)values, op.d_masks, op.n_cells, transpose); \
+    break;
+  switch (op.degree)
+    {
+      HN_CASE(2) HN_CASE(3) HN_CASE(4) HN_CASE(5) HN_CASE(6) HN_CASE(7) HN_CASE(8) HN_CASE(9)
+    }
+#undef HN_CASE
+  CUDA_CHECK(cudaGetLastError());
+  ++op.launches;
+}
+
+template <typename Number>
+__global__ void fma_bench_kernel(Number *out, int iters)
+{
+  Number a[8], x = Number(1.0) + Number(1e-9) * threadIdx.x, y = Number(0.5);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = Number(i) * Number(0.125) + x;
+  for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = a[i] * x + y;
+    }
+  Number s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == Number(-1)) out[0] = s;
+}
+} // namespace mfhn
+
+using namespace mfhn;
+
+extern "C" {
+int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out)
+{
+  return guard([&] {
+    if (!desc || !out) throw InvalidArgument("null argument");
+    *out = reinterpret_cast<mfhn_op>(op_create(*desc));
+  });
+}
+void mfhn_op_destroy(mfhn_op op) { delete reinterpret_cast<Operator *>(op); }
+
+int mfhn_op_vmult(mfhn_op h, void *dst, const void *src, void *stream, int zero_dst)
+{
+  return guard([&] {
+    if (!h || !dst || !src) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (zero_dst)
+      CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)(op.n_owned + op.n_ghost) * (op.number == MFHN_F64 ? 8 : 4), st));
+    op_vmult_range(op, dst, src, st, 0, op.n_cells);
+  });
+}
+int mfhn_op_vmult_range(mfhn_op h, void *dst, const void *src, void *stream, int64_t cb, int64_t ce)
+{
+  return guard([&] {
+    if (!h || !dst || !src) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    op_vmult_range(op, dst, src, static_cast<cudaStream_t>(stream), cb, ce);
+  });
+}
+int mfhn_op_set_apply_constraints(mfhn_op h, int v)
+{
+  return guard([&] {
+    if (!h) throw InvalidArgument("null argument");
+    reinterpret_cast<Operator *>(h)->apply_constraints = v != 0;
+  });
+}
+int mfhn_op_set_kernel(mfhn_op h, int kernel)
+{
+  return guard([&] {
+    if (!h) throw InvalidArgument("null argument");
+    Operator &op  = *reinterpret_cast<Operator *>(h);
+    const int old = op.kernel;
+    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_PLANE) throw InvalidArgument("unknown kernel");
+    op.kernel = kernel;
+    try
+      {
+        resolve_kernel(op);
+      }
+    catch (...)
+      {
+        op.kernel = old;
+        throw;
+      }
+  });
+}
+int mfhn_op_apply_hn(mfhn_op h, void *values, int transpose, void *stream)
+{
+  return guard([&] {
+    if (!h || !values) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    if (op.number == MFHN_F64)
+      hn_only<double>(op, values, transpose, static_cast<cudaStream_t>(stream));
+    else
+      hn_only<float>(op, values, transpose, static_cast<cudaStream_t>(stream));
+  });
+}
+int mfhn_op_query(mfhn_op h, const char *what, double *value)
+{
+  return guard([&] {
+    if (!h || !what || !value) throw InvalidArgument("null argument");
+    const Operator &op = *reinterpret_cast<Operator *>(h);
+    const double n = op.degree + 1, n3 = n * n * n, s = op.number == MFHN_F64 ? 8 : 4;
+    const double nvec = (double)(op.n_owned + op.n_ghost);
+    const std::string w(what);
+    if (w == "n_cells")
+      *value = (double)op.n_cells;
+    else if (w == "n_cells_hn")
+      *value = (double)op.n_cells_hn;
+    else if (w == "algorithmic_bytes") // 2 s n_dofs + n_cells (4 (k+1)^3 + 1 + G)
+      *value = 2 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : 10 * s));
+    else if (w == "algorithmic_flops") // even-odd sum factorisation count of SURVEY 8d, without HN terms
+      *value = (double)op.n_cells * (12 * n * n * (n * n + 2 * n) + 3 * n3);
+    else if (w == "kernel")
+      *value = (double)resolve_kernel(op);
+    else
+      throw InvalidArgument("unknown query '" + w + "'");
+  });
+}
+int64_t mfhn_op_launch_count(mfhn_op h) { return h ? reinterpret_cast<Operator *>(h)->launches : 0; }
+
+int mfhn_pack(int number, void *buffer, const void *vec, const int32_t *idx, int64_t n, void *stream)
+{
+  return guard([&] {
+    if (n <= 0) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cudaStream_t st     = static_cast<cudaStream_t>(stream);
+    if (number == MFHN_F64)
+      pack_kernel<double><<<grid, 256, 0, st>>>((double *)buffer, (const double *)vec, idx, n);
+    else
+      pack_kernel<float><<<grid, 256, 0, st>>>((float *)buffer, (const float *)vec, idx, n);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+int mfhn_unpack_add(int number, void *vec, const void *buffer, const int32_t *idx, int64_t n, void *stream)
+{
+  return guard([&] {
+    if (n <= 0) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cudaStream_t st     = static_cast<cudaStream_t>(stream);
+    if (number == MFHN_F64)
+      unpack_add_kernel<double><<<grid, 256, 0, st>>>((double *)vec, (const double *)buffer, idx, n);
+    else
+      unpack_add_kernel<float><<<grid, 256, 0, st>>>((float *)vec, (const float *)buffer, idx, n);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+int mfhn_bench_dfma(int number, int iters, double *tflops)
+{
+  return guard([&] {
+    if (!tflops) throw InvalidArgument("null argument");
+    void *out = nullptr;
+    CUDA_CHECK(cudaMalloc(&out, 64));
+    cudaDeviceProp prop;
+    int dev;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep)
+      {
+        CUDA_CHECK(cudaEventRecord(e0));
+        if (number == MFHN_F64)
+          fma_bench_kernel<double><<<blocks, threads>>>((double *)out, iters);
+        else
+          fma_bench_kernel<float><<<blocks, threads>>>((float *)out, iters);
+        CUDA_CHECK(cudaEventRecord(e1));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+      }
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+  });
+}
+}

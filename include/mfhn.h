@@ -1,0 +1,179 @@
+/*
+ * mfhn.h -- C ABI of the B200-native matrix-free hanging-node operator engine.
+ *
+ * This is the drop-in boundary for the hot path of
+ * peterrum/dealii-matrixfree-hanging-nodes: the 3D Laplace vmult on FE_Q(k),
+ * k = 1..8, on octree meshes with hanging-node constraints.  Plain pointers and
+ * sizes only; no C++ or torch types cross it.  Every entry point returns an
+ * int status (0 = ok) and never throws; mfhn_last_error() gives the message.
+ *
+ * Each entry point cites the reference interface (file:line in the reference
+ * repository) it stands in for.  The arithmetic behind those interfaces lives
+ * in deal.II (not vendored by the reference), see DESIGN.md.
+ */
+#ifndef MFHN_H
+#define MFHN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFHN_OK 0
+#define MFHN_ERR_INVALID 1     /* bad argument (e.g. unsupported degree, unknown geometry) */
+#define MFHN_ERR_CUDA 2        /* CUDA runtime failure */
+#define MFHN_ERR_NOT_IMPL 3    /* like the reference's ExcNotImplemented */
+
+typedef struct mfhn_mesh_s *mfhn_mesh;
+typedef struct mfhn_dofs_s *mfhn_dofs;
+typedef struct mfhn_op_s *mfhn_op;
+
+/* number types (reference: `using Number = double`, benchmark_03.h:390) */
+#define MFHN_F64 0
+#define MFHN_F32 1
+
+/* mesh flavours: which 2:1 balance the refinement enforces */
+#define MFHN_SERIAL 0 /* dealii::Triangulation: faces + edges  (benchmark_01.h:183)           */
+#define MFHN_P4EST 1  /* parallel::distributed::Triangulation: + corners (benchmark_03.h:397) */
+
+/* geometry descriptions accepted by mfhn_op_create */
+#define MFHN_GEOM_CARTESIAN 0 /* one double per cell: edge length h                       */
+#define MFHN_GEOM_AFFINE 1    /* nine doubles per cell: Jacobian J[r][c] = dx_r/dxi_c      */
+
+/* cell kernels */
+#define MFHN_KERNEL_AUTO 0
+#define MFHN_KERNEL_QPOINT 1    /* collocation sum factorisation + quadrature-point operation */
+#define MFHN_KERNEL_SEPARABLE 2 /* Cartesian cells only: 1D mass/stiffness tensor form        */
+#define MFHN_KERNEL_BASELINE 3  /* restatement of the deal.II CUDA design (one thread per DoF) */
+#define MFHN_KERNEL_PLANE 4     /* Cartesian cells, register-tiled separable kernel (fast path)  */
+
+const char *mfhn_last_error(void);
+const char *mfhn_version(void);
+
+/* ---------------------------------------------------------------------------
+ * Mesh layer.  Replaces GridGenerator::create_{quadrant,annulus,step,
+ * quadrant_flexible} on hyper_cube(-1,1)^3   (reference benchmark.h:7-144,
+ * benchmark_03.h:26-104).
+ * ------------------------------------------------------------------------ */
+int mfhn_mesh_create(const char *geometry, int n_refinements, int flavour, mfhn_mesh *out);
+void mfhn_mesh_destroy(mfhn_mesh m);
+int64_t mfhn_mesh_n_cells(mfhn_mesh m);  /* tria.n_active_cells()   benchmark_01.h:302 */
+int mfhn_mesh_n_levels(mfhn_mesh m);     /* tria.n_global_levels()  benchmark_03.h:406 */
+/* Active cells in storage order: out[4*c + {0,1,2,3}] = level, ix, iy, iz. */
+int mfhn_mesh_cells(mfhn_mesh m, int32_t *out);
+/* Number of cells with hanging nodes: Helper::is_constrained
+ * (constraint_helper.h:89-125; counted in benchmark_03.h:415-432). */
+int64_t mfhn_mesh_n_cells_hn(mfhn_mesh m);
+/* Morton-curve partition of the active cells into n_ranks contiguous chunks of
+ * equal weight; weight = 1 + 10*w for hanging-node cells, 11 otherwise
+ * (benchmark_02.cc:15-37; w == 1 gives the plain p4est partition).
+ * rank_of_cell is in storage order. */
+int mfhn_mesh_partition(mfhn_mesh m, int n_ranks, double hn_weight, int32_t *rank_of_cell);
+/* Position of every active cell (storage order) along the Morton curve. */
+int mfhn_mesh_morton_position(mfhn_mesh m, int64_t *position_of_cell);
+
+/* ---------------------------------------------------------------------------
+ * DoF layer.  Replaces DoFHandler::distribute_dofs(FE_Q(degree)) and the
+ * index / mask part of MatrixFree::reinit  (benchmark_01.h:247,255-256;
+ * benchmark_03.h:227-228,338-339,438-439).
+ * With rank_of_cell == NULL (or n_ranks == 1) the numbering is the serial one.
+ * ------------------------------------------------------------------------ */
+int mfhn_dofs_create(mfhn_mesh m, int degree, int n_ranks, const int32_t *rank_of_cell,
+                     mfhn_dofs *out);
+void mfhn_dofs_destroy(mfhn_dofs d);
+int64_t mfhn_dofs_n_dofs(mfhn_dofs d); /* dof_handler.n_dofs()  benchmark_03.h:441 */
+/* Global range [begin,end) owned by rank. */
+int mfhn_dofs_owned_range(mfhn_dofs d, int rank, int64_t *begin, int64_t *end);
+int64_t mfhn_dofs_n_cells_of_rank(mfhn_dofs d, int rank);
+/* Storage-order indices of the cells of `rank`, ascending. */
+int mfhn_dofs_cells_of_rank(mfhn_dofs d, int rank, int64_t *cell_ids);
+/* Fill the arrays for the n cells listed in cell_ids (storage-order indices,
+ * any order -- MatrixFree is free to reorder its cell batches).  Any output
+ * pointer may be NULL.
+ *   raw_indices  uint64[n*(k+1)^3]   lexicographic, global, before substitution
+ *   dof_indices  uint64[n*(k+1)^3]   lexicographic, global, coarse-substituted
+ *   masks        uint8[n]            compressed_constraint_kind
+ *                                    (dof_info.hanging_node_constraint_masks, benchmark_01.h:335)
+ *   h            double[n]           cell edge length */
+int mfhn_dofs_fill(mfhn_dofs d, int64_t n, const int64_t *cell_ids, uint64_t *raw_indices,
+                   uint64_t *dof_indices, uint8_t *masks, double *h);
+/* Support points (x,y,z) of the DoFs in [begin,end) -- what
+ * VectorTools::interpolate needs (benchmark_03.h:459-461). */
+int mfhn_dofs_support_points(mfhn_dofs d, int64_t begin, int64_t end, double *xyz);
+
+/* ConstraintKinds <-> compressed byte (deal.II hanging_nodes_internal.h,
+ * used at benchmark_00_likwid.cc:45-48). */
+uint8_t mfhn_compress(uint16_t kind);
+uint16_t mfhn_decompress(uint8_t compressed);
+int mfhn_check_kind(uint16_t kind);
+
+/* ---------------------------------------------------------------------------
+ * Operator.  Replaces LaplaceOperator<3,degree,Number,MemorySpace::CUDA>
+ * (benchmark_03.h:319-357): constructor = CUDAWrappers::MatrixFree::reinit,
+ * vmult = cell_loop(LaplaceOperatorLocal, src, dst).
+ * ------------------------------------------------------------------------ */
+typedef struct
+{
+  int degree;                  /* 1..8 (reference dispatches 1..6, benchmark_03.h:565-614)   */
+  int number;                  /* MFHN_F64 / MFHN_F32                                         */
+  int64_t n_cells;             /* cells of this rank                                          */
+  int64_t n_owned;             /* locally owned DoFs: vector entries [0,n_owned)              */
+  int64_t n_ghost;             /* ghost DoFs: vector entries [n_owned,n_owned+n_ghost)        */
+  const uint32_t *dof_indices; /* [n_cells*(k+1)^3] rank-local, lexicographic, substituted     */
+  const uint8_t *masks;        /* [n_cells] compressed_constraint_kind                         */
+  int geometry_type;           /* MFHN_GEOM_*                                                  */
+  const double *geometry;      /* per-cell geometry, see MFHN_GEOM_*                           */
+  int apply_constraints;       /* benchmark_03.h:255-268: false => plain gather/scatter        */
+  int kernel;                  /* MFHN_KERNEL_*                                                */
+  int device;                  /* CUDA device ordinal, -1 = current                            */
+} mfhn_op_desc;
+
+int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out);
+void mfhn_op_destroy(mfhn_op op);
+
+/* dst (+)= A src on device vectors of n_owned+n_ghost entries of the operator's
+ * Number type.  Stream-ordered and asynchronous like the reference's cell_loop
+ * (the benchmark synchronises explicitly, benchmark_03.h:485).  zero_dst == 0
+ * accumulates exactly like the reference (benchmark_03.h:240,352); zero_dst != 0
+ * clears dst first inside the same stream.
+ * cell_begin/cell_end select a sub-range of the operator's cells (used to
+ * overlap the ghost exchange with interior cells); pass 0, -1 for all. */
+int mfhn_op_vmult(mfhn_op op, void *dst, const void *src, void *cuda_stream, int zero_dst);
+int mfhn_op_vmult_range(mfhn_op op, void *dst, const void *src, void *cuda_stream,
+                        int64_t cell_begin, int64_t cell_end);
+
+/* Change the apply_constraints switch / kernel of an existing operator. */
+int mfhn_op_set_apply_constraints(mfhn_op op, int apply_constraints);
+int mfhn_op_set_kernel(mfhn_op op, int kernel);
+
+/* Hanging-node interpolation alone on cell-local values (device pointer,
+ * [n_cells][(k+1)^3]): FEEvaluationHangingNodesFactory::apply
+ * (benchmark_00_likwid.cc:56-59). */
+int mfhn_op_apply_hn(mfhn_op op, void *cell_values, int transpose, void *cuda_stream);
+
+/* Queries: algorithmic bytes / flops of one vmult, cell counts. */
+int mfhn_op_query(mfhn_op op, const char *what, double *value);
+/* Number of kernels launched by this operator since creation. */
+int64_t mfhn_op_launch_count(mfhn_op op);
+
+/* ---------------------------------------------------------------------------
+ * Distributed-vector helpers.  Replace the device side of
+ * LinearAlgebra::distributed::Vector<Number,MemorySpace::CUDA>::
+ * update_ghost_values / compress(add)  (benchmark_03.h:323-324, used inside
+ * CUDAWrappers::MatrixFree::cell_loop): pack owned entries into a send buffer,
+ * add received contributions.
+ * ------------------------------------------------------------------------ */
+int mfhn_pack(int number, void *buffer, const void *vec, const int32_t *indices_dev, int64_t n,
+              void *cuda_stream);
+int mfhn_unpack_add(int number, void *vec, const void *buffer, const int32_t *indices_dev,
+                    int64_t n, void *cuda_stream);
+
+/* Microbenchmarks used for the roofline denominators (bench.py). */
+int mfhn_bench_dfma(int number, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFHN_H */

@@ -1,0 +1,193 @@
+"""Parity of the CUDA vmult (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): 1e-12 relative in double, 1e-5 in float,
+max-norm scaled by ||A src||_inf.  DoF indices and masks are compared bit-exact
+in test_setup_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import dofs, mesh, operators
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-12, "float": 1e-5}
+
+
+def _case(mfhn, geo, L, flavour, k):
+    tria = mfhn.Triangulation(geo, L, flavour)
+    dh = mfhn.DoFHandler(tria, k)
+    mf = mfhn.MatrixFree(dh)
+    lay = dofs.setup(mesh.create(geo, L, flavour), k)
+    return dh, mf, lay
+
+
+def _src(lay, kind):
+    if kind == "sin":  # benchmark_03.h:362-378
+        return np.sin(lay.support_points).sum(axis=1)
+    return np.random.default_rng(12345).uniform(-1, 1, lay.n_dofs)
+
+
+def _run(mfhn, mf, x, number, kernel, apply_constraints=True):
+    import torch
+
+    op = mfhn.LaplaceOperator(mf, number=number, kernel=kernel, apply_constraints=apply_constraints)
+    src = op.initialize_dof_vector()
+    dst = op.initialize_dof_vector()
+    src.copy_(torch.from_numpy(x).to(src.dtype))
+    op.vmult(dst, src)
+    torch.cuda.synchronize()
+    return dst.cpu().numpy().astype(np.float64), op
+
+
+KERNELS = ["qpoint", "separable", "plane"]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_vmult_matches_oracle_annulus(mfhn, k, kernel, number):
+    if kernel == "plane" and k > 5:
+        pytest.skip("register-tiled kernel covers degree <= 5")
+    L = 5 if k <= 4 else 4 if k <= 6 else 3
+    geo = "annulus" if k <= 4 else "quadrant"
+    dh, mf, lay = _case(mfhn, geo, L, "serial", k)
+    for kind in ("sin", "random"):
+        x = _src(lay, kind)
+        ref = operators.vmult_fast(lay, x)
+        y, _ = _run(mfhn, mf, x, number, kernel)
+        err = np.abs(y - ref).max() / np.abs(ref).max()
+        assert err < TOL[number], (k, kernel, number, kind, err)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_vmult_without_constraints(mfhn, kernel):
+    """apply_constraints=false: plain gather/scatter on the same index arrays
+    (benchmark_03.h:255-268)."""
+    dh, mf, lay = _case(mfhn, "annulus", 5, "p4est", 3)
+    x = _src(lay, "random")
+    ref = operators.vmult_fast(lay, x, apply_constraints=False)
+    y, _ = _run(mfhn, mf, x, "double", kernel, apply_constraints=False)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_vmult_accumulates_like_reference(mfhn):
+    """cell_loop passes no zero flag (benchmark_03.h:352): dst += A src."""
+    import torch
+
+    dh, mf, lay = _case(mfhn, "quadrant", 3, "serial", 2)
+    x = _src(lay, "random")
+    op = mfhn.LaplaceOperator(mf)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.copy_(torch.from_numpy(x))
+    op.vmult(dst, src)
+    op.vmult(dst, src)
+    once = operators.vmult_fast(lay, x)
+    assert np.abs(dst.cpu().numpy() - 2 * once).max() / np.abs(once).max() < 1e-12
+    op.vmult(dst, src, zero_dst=True)
+    assert np.abs(dst.cpu().numpy() - once).max() / np.abs(once).max() < 1e-12
+
+
+def test_constant_is_in_null_space_large(mfhn):
+    """A 1 = 0 (src == 1 is what benchmark_01.h:510-511 times) at a size the oracle
+    would not finish quickly: size-independent property."""
+    import torch
+
+    tria = mfhn.Triangulation("annulus", 7, "p4est")
+    dh = mfhn.DoFHandler(tria, 4)
+    mf = mfhn.MatrixFree(dh)
+    for kernel in KERNELS:
+        op = mfhn.LaplaceOperator(mf, kernel=kernel)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.fill_(1.0)
+        op.vmult(dst, src)
+        assert dst.abs().max().item() < 1e-11
+
+
+def test_symmetry_and_energy_large(mfhn):
+    """x^T A y = y^T A x and u^T A u = int |grad p|^2 for a polynomial p of degree <= k
+    on a mesh with hanging nodes (exact for the conforming space)."""
+    import torch
+
+    tria = mfhn.Triangulation("quadrant", 5, "p4est")
+    k = 3
+    dh = mfhn.DoFHandler(tria, k)
+    mf = mfhn.MatrixFree(dh)
+    pts = dh.support_points()
+    X, Y, Z = pts[:, 0], pts[:, 1], pts[:, 2]
+    p = X * X + Y * Z + 0.5 * X * Y * Z + X * Y * Y
+    # int over (-1,1)^3 of |grad p|^2 with grad p = (2x + yz/2 + y^2, z + xz/2 + 2xy, y + xy/2)
+    import sympy as sp
+
+    x, y, z = sp.symbols("x y z")
+    pe = x * x + y * z + sp.Rational(1, 2) * x * y * z + x * y * y
+    exact = float(sp.integrate(sum(sp.diff(pe, v) ** 2 for v in (x, y, z)), (x, -1, 1), (y, -1, 1), (z, -1, 1)))
+    rng = np.random.default_rng(12345)
+    a, b = rng.uniform(-1, 1, dh.n_dofs()), rng.uniform(-1, 1, dh.n_dofs())
+    for kernel in KERNELS:
+        op = mfhn.LaplaceOperator(mf, kernel=kernel)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+
+        def A(v):
+            src.copy_(torch.from_numpy(v))
+            op.vmult(dst, src, zero_dst=True)
+            return dst.cpu().numpy()
+
+        Ap = A(p)
+        # hanging entries of dst are never written and hanging entries of src never read:
+        # the energy uses the live entries only
+        assert abs(p @ Ap - exact) / exact < 1e-12, (kernel, p @ Ap, exact)
+        Aa, Ab = A(a), A(b)
+        live = Aa != 0
+        assert abs(b[live] @ Aa[live] - a[live] @ Ab[live]) / abs(b[live] @ Aa[live]) < 1e-10
+
+
+def test_affine_geometry_matches_cartesian(mfhn):
+    """Affine path with J = h I must reproduce the Cartesian result; a sheared J
+    must stay symmetric and keep constants in the null space."""
+    import torch
+
+    dh, mf, lay = _case(mfhn, "annulus", 5, "serial", 2)
+    x = _src(lay, "random")
+    ref = operators.vmult_fast(lay, x)
+    J = np.einsum("c,ij->cij", mf.h, np.eye(3))
+    op = mfhn.LaplaceOperator(mf, kernel="qpoint", geometry=J)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.copy_(torch.from_numpy(x))
+    op.vmult(dst, src)
+    assert np.abs(dst.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_hanging_node_kernel_alone(mfhn):
+    """FEEvaluationHangingNodesFactory::apply analogue (benchmark_00_likwid.cc:56-59)."""
+    import torch
+
+    for k in (1, 2, 4, 7):
+        dh, mf, lay = _case(mfhn, "annulus", 5 if k < 7 else 4, "serial", k)
+        op = mfhn.LaplaceOperator(mf)
+        n = k + 1
+        rng = np.random.default_rng(7)
+        vals = rng.uniform(-1, 1, (mf.n_cells, n, n, n))
+        # mf cells are reordered: recover kinds from the masks
+        kinds = np.array([dofs.decompress(int(m)) for m in mf.masks], dtype=np.uint16)
+        for transpose in (False, True):
+            d = torch.from_numpy(vals.copy()).cuda()
+            op.apply_hanging_node_constraints(d, transpose)
+            ref = operators.hn_apply(vals.copy(), kinds, k, transpose)
+            assert np.abs(d.cpu().numpy() - ref).max() < 1e-13
+
+
+def test_error_behaviour(mfhn):
+    """Unsupported inputs raise like the reference's AssertThrow paths."""
+    with pytest.raises(mfhn.MfhnError):
+        mfhn.Triangulation("torus", 3)  # "Unknown geometry type!" benchmark_03.h:404
+    tria = mfhn.Triangulation("quadrant", 2, "serial")
+    with pytest.raises(mfhn.MfhnError):
+        mfhn.DoFHandler(tria, 9)  # degree dispatch default case, benchmark_01.cc:64-66
+    dh = mfhn.DoFHandler(tria, 6)
+    mf = mfhn.MatrixFree(dh)
+    with pytest.raises(mfhn.MfhnError):
+        mfhn.LaplaceOperator(mf, kernel="plane")  # not available for this degree
+    op = mfhn.LaplaceOperator(mf)
+    v = op.initialize_dof_vector()
+    with pytest.raises(mfhn.MfhnError):
+        op.vmult(v, v)
