@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: 3D Laplace vmult, FE_Q(k), adaptively refined mesh
+with hanging nodes (reference driver: benchmark_03.h:382-546, `./benchmark_03
+cuda annulus 4`, cuda/run.sh).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA engine
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference
+
+Prints ONE JSON line (rank 0).  metric = Laplace vmult throughput in GDoF/s,
+n_dofs = dof_handler.n_dofs() as tabulated by the reference (benchmark_03.h:441).
+A step is one vmult (dst += A src, accumulating like benchmark_03.h:352) over
+the whole mesh.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "dealii-matrixfree-hanging-nodes_b200"
+
+METRIC = "laplace_vmult_throughput"
+UNIT = "GDoF/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)  # n_repetitions = 100, benchmark_03.h:393
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--geometry", default="annulus")
+    ap.add_argument("--refinements", type=int, default=None)
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--number", default="double", choices=["double", "float"])
+    ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--sweep", action="store_true", help="also time degrees 1..8 and the kernel variants (extra keys)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def default_refinements(args):
+    if args.refinements is not None:
+        return args.refinements
+    # SURVEY 8d / BASELINE.md C2: annulus (p4est flavour) L=9 for k <= 4 (142.8 M DoFs at k=4), L=8 for k >= 5
+    if args.geometry == "annulus":
+        return 9 if args.degree <= 4 else 8
+    return 8 if args.degree <= 4 else 7
+
+
+def time_vmult(torch, op, dst, src, steps, warmup, barrier=None):
+    """K steps bracketed by synchronize (+barrier), per-launch CUDA events on the launching stream."""
+    for _ in range(warmup):
+        op.vmult(dst, src)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(steps):
+        op.vmult(dst, src)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])  # ms
+    return ev[0].elapsed_time(ev[steps]), per
+
+
+def cpu_sample(mf, n_sample_cells):
+    """Bounded sample of the workload for the CPU arm: the first cells along the
+    Morton curve with their DoFs renumbered compactly."""
+    ns = min(n_sample_cells, mf.n_cells)
+    idx = mf.dof_indices[:ns]
+    uniq, inv = np.unique(idx, return_inverse=True)
+    return inv.reshape(idx.shape).astype(np.uint32), mf.masks[:ns], mf.h[:ns], len(uniq), ns
+
+
+def run_cpu(args, mf, degree, n_rep, n_sample_cells=200_000, threads=None):
+    from oracle import cpu
+
+    threads = threads or os.cpu_count()
+    idx, masks, h, nd, ns = cpu_sample(mf, n_sample_cells)
+    t = cpu.benchmark(degree, idx, masks, h, nd, True, n_rep, threads)
+    return {"value": threads * nd / t / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {ns} cells of the Morton curve ({nd} DoFs) of the same mesh, src=1, {n_rep} reps per thread, "
+                      f"every thread applies the operator to its own vectors (benchmark_01.h:536-573); "
+                      f"C restatement of the deal.II CPU path, not deal.II"}, t, nd
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    L = default_refinements(args)
+    workload = f"{args.geometry} L={L} (p4est-balanced octree on hyper_cube(-1,1)^3), FE_Q({args.degree}), {args.number}, Cartesian MappingQ1"
+
+    mfhn = importlib.import_module(PKG)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        tria = mfhn.Triangulation(args.geometry, L, "p4est")
+        dh = mfhn.DoFHandler(tria, args.degree)
+        mf = mfhn.MatrixFree(dh)
+        from oracle import cpu
+
+        threads = os.cpu_count()
+        idx, masks, h, nd, ns = cpu_sample(mf, 200_000)
+        for _ in range(max(args.warmup, 0)):
+            cpu.benchmark(args.degree, idx, masks, h, nd, True, 1, threads)
+        t0 = time.perf_counter()
+        t = cpu.benchmark(args.degree, idx, masks, h, nd, True, args.steps, threads)
+        wall = time.perf_counter() - t0
+        v = threads * nd / t / 1e9
+        cb = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+              "sample": f"first {ns} cells of the Morton curve ({nd} DoFs per replica) of the same mesh; every thread applies the operator "
+                        f"to its own vectors (benchmark_01.h:536-573); C restatement of the deal.II CPU path (deal.II itself cannot be built here)"}
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "n_dofs": dh.n_dofs()},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "wall_s": wall}))
+        return
+
+    import torch
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    barrier = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        barrier = dist.barrier
+
+    t_setup = time.perf_counter()
+    from bench_dist import build_problem  # noqa: E402  (shared by the 1-GPU and the partitioned path)
+
+    prob = build_problem(mfhn, args, L, rank, world)
+    op, mf, n_dofs_global = prob["op"], prob["mf"], prob["n_dofs"]
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    prob["fill_src"](src)
+    t_setup = time.perf_counter() - t_setup
+
+    with ClockSampler(local_rank) as clocks:
+        total_ms, per = time_vmult(torch, op, dst, src, args.steps, args.warmup, barrier)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_dofs_global / (ms_per_step * 1e-3) / 1e9
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic"}
+    launches_per_step = prob["launches_per_step"]
+    out["gpu_launches"] = int(launches_per_step * args.steps)
+
+    # roofline of the dominant kernel (the fused cell kernel): algorithmic bytes / average launch time
+    peak, peak_src = peaks()
+    b_alg = op.query("algorithmic_bytes")
+    kernel_ms = float(np.mean(per)) if world == 1 else ms_per_step
+    achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                       "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
+                       "kernel_ms_min_avg_max": [float(per.min()), float(per.mean()), float(per.max())],
+                       "algorithmic_flops_per_launch": op.query("algorithmic_flops")}
+    out["clocks"] = clocks.summary()
+    out["config"] = {"workload": workload, "n_cells": int(prob["n_cells_global"]), "n_cells_hn": int(prob["n_cells_hn_global"]),
+                     "n_dofs": int(n_dofs_global), "kernel": prob["kernel_name"], "partition": prob["partition"],
+                     "l2": "inputs larger than L2 (vectors + index arrays >> 126 MB), no flush",
+                     "dst": "accumulating vmult like benchmark_03.h:352", "setup_s": round(t_setup, 1)}
+
+    if rank == 0 and world == 1:
+        # hanging-node overhead on the same mesh and index arrays (benchmark_03.h:255-268)
+        op.set_apply_constraints(False)
+        _, per_nc = time_vmult(torch, op, dst, src, max(args.steps // 2, 5), 3)
+        op.set_apply_constraints(True)
+        out["hn_overhead_percent"] = 100.0 * (float(np.mean(per)) / float(np.mean(per_nc)) - 1.0)
+        out["no_constraints_gdofs"] = n_dofs_global / (float(np.mean(per_nc)) * 1e-3) / 1e9
+        # the other kernels on the same problem, for the record
+        variants = {}
+        for kname in ("qpoint", "separable"):
+            try:
+                op.set_kernel(kname)
+                _, pk = time_vmult(torch, op, dst, src, 10, 3)
+                variants[kname] = n_dofs_global / (float(np.mean(pk)) * 1e-3) / 1e9
+            except mfhn.MfhnError as e:
+                variants[kname] = str(e)
+        op.set_kernel(args.kernel)
+        out["kernel_variants_gdofs"] = variants
+        out["fp64_fma_tflops_measured"] = mfhn.bench_fma("double", 20000)
+
+    if not args.no_e2e:
+        # end to end through the host-vector entry point: H2D of src, kernel, D2H of dst every step
+        n_local = src.numel()
+        hs = torch.empty(n_local, dtype=src.dtype).pin_memory()
+        hd = torch.empty(n_local, dtype=src.dtype).pin_memory()
+        hs.copy_(src.cpu())
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            op.vmult_host(hd, hs, zero_dst=True)
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e_steps):
+            op.vmult_host(hd, hs, zero_dst=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        esz = src.element_size()
+        out["e2e"] = {"value": n_dofs_global / (e_ms / e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_local * esz),
+                      "d2h_bytes_per_step": int(n_local * esz), "steps": e_steps,
+                      "note": "mfhn_op_vmult_host: pinned host src -> device, vmult into a zeroed device dst, dst -> pinned host; PCIe-bound"}
+        if world > 1:
+            out["e2e"]["note"] += "; per-rank local vectors, no ghost exchange on this path"
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _, _ = run_cpu(args, mf, args.degree, 5)
+        out["cpu_baseline"] = cb
+
+    if args.sweep and world == 1 and rank == 0:
+        from bench_dist import degree_sweep
+
+        out["degree_sweep"] = degree_sweep(mfhn, torch, args, time_vmult)
+
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -139,12 +139,15 @@ struct Operator
   void *d_geom = nullptr;       // Number h[cell] or Number G[cell][6]
   PlaneLayout plane;            // warp-interleaved layout of the register-tiled kernel
   long long launches = 0;
+  void *d_stage_src = nullptr, *d_stage_dst = nullptr; // device staging of the host-buffer entry point
 
   ~Operator()
   {
     cudaFree(d_idx);
     cudaFree(d_masks);
     cudaFree(d_geom);
+    cudaFree(d_stage_src);
+    cudaFree(d_stage_dst);
     plane.free();
   }
 };
@@ -422,6 +425,28 @@ int mfhn_op_vmult_range(mfhn_op h, void *dst, const void *src, void *stream, int
     Operator &op = *reinterpret_cast<Operator *>(h);
     CUDA_CHECK(cudaSetDevice(op.device));
     op_vmult_range(op, dst, src, static_cast<cudaStream_t>(stream), cb, ce);
+  });
+}
+int mfhn_op_vmult_host(mfhn_op h, void *dst_host, const void *src_host, void *stream, int zero_dst)
+{
+  return guard([&] {
+    if (!h || !dst_host || !src_host) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    cudaStream_t st    = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)(op.n_owned + op.n_ghost) * (op.number == MFHN_F64 ? 8 : 4);
+    if (!op.d_stage_src)
+      {
+        CUDA_CHECK(cudaMalloc(&op.d_stage_src, std::max<size_t>(bytes, 8)));
+        CUDA_CHECK(cudaMalloc(&op.d_stage_dst, std::max<size_t>(bytes, 8)));
+      }
+    CUDA_CHECK(cudaMemcpyAsync(op.d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, st));
+    if (zero_dst)
+      CUDA_CHECK(cudaMemsetAsync(op.d_stage_dst, 0, bytes, st));
+    else
+      CUDA_CHECK(cudaMemcpyAsync(op.d_stage_dst, dst_host, bytes, cudaMemcpyHostToDevice, st));
+    op_vmult_range(op, op.d_stage_dst, op.d_stage_src, st, 0, op.n_cells);
+    CUDA_CHECK(cudaMemcpyAsync(dst_host, op.d_stage_dst, bytes, cudaMemcpyDeviceToHost, st));
   });
 }
 int mfhn_op_set_apply_constraints(mfhn_op h, int v)

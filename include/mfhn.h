@@ -144,6 +144,14 @@ int mfhn_op_vmult(mfhn_op op, void *dst, const void *src, void *cuda_stream, int
 int mfhn_op_vmult_range(mfhn_op op, void *dst, const void *src, void *cuda_stream,
                         int64_t cell_begin, int64_t cell_end);
 
+/* Same operation on HOST vectors (pinned memory recommended): copies src (and
+ * dst unless zero_dst) to the device, applies the operator, copies dst back.
+ * All copies are issued asynchronously on cuda_stream; synchronise the stream
+ * before reading dst.  This is the call a host-vector caller such as
+ * LaplaceOperator<...,MemorySpace::Host>::vmult (benchmark_03.h:237-241) binds. */
+int mfhn_op_vmult_host(mfhn_op op, void *dst_host, const void *src_host, void *cuda_stream,
+                       int zero_dst);
+
 /* Change the apply_constraints switch / kernel of an existing operator. */
 int mfhn_op_set_apply_constraints(mfhn_op op, int apply_constraints);
 int mfhn_op_set_kernel(mfhn_op op, int kernel);
