@@ -34,7 +34,7 @@ def build_problem(mfhn, args, L, rank, world):
         i = torch.arange(src.numel(), device=src.device, dtype=torch.float64)
         src.copy_(torch.sin(1e-3 * i).to(src.dtype))
 
-    kname = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane"}[int(op.query("kernel"))]
+    kname = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch"}[int(op.query("kernel"))]
     return {"op": op, "mf": mf, "dh": dh, "tria": tria, "n_dofs": dh.n_dofs(), "n_cells_global": tria.n_active_cells(),
             "n_cells_hn_global": tria.n_cells_with_hanging_nodes(), "fill_src": fill_src, "kernel_name": kname,
             "partition": partition, "launches_per_step": launches, "comm": comm}
@@ -54,7 +54,7 @@ def degree_sweep(mfhn, torch, args, time_vmult):
             op = mfhn.LaplaceOperator(mf, number=number)
             src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
             src.fill_(1.0)
-            for kern in ("plane", "separable", "qpoint"):
+            for kern in ("patch", "plane", "separable", "qpoint"):
                 try:
                     op.set_kernel(kern)
                 except mfhn.MfhnError:

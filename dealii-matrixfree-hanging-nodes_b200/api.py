@@ -238,8 +238,9 @@ class LaplaceOperator:
         self.dtype = _TORCH_DTYPE[self.number]
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         part = matrix_free.partitioner
-        kern = {"auto": capi.KERNEL_AUTO, "qpoint": capi.KERNEL_QPOINT, "separable": capi.KERNEL_SEPARABLE,
-                "baseline": capi.KERNEL_BASELINE, "plane": capi.KERNEL_PLANE}[kernel]
+        kern = capi.KERNELS[kernel]
+        ni = matrix_free.n_interior_cells
+        self._segments = np.array([0, ni] if 0 < ni < matrix_free.n_cells else [0], dtype=np.int64)
         if geometry is None:
             gtype, geom = capi.GEOM_CARTESIAN, matrix_free.h
         else:  # (n_cells, 3, 3) Jacobians
@@ -249,7 +250,7 @@ class LaplaceOperator:
             degree=matrix_free.degree, number=self.number, n_cells=matrix_free.n_cells, n_owned=part.n_owned,
             n_ghost=part.n_ghost, dof_indices=_ptr(matrix_free.dof_indices), masks=_ptr(matrix_free.masks),
             geometry_type=gtype, geometry=_ptr(geom), apply_constraints=int(apply_constraints), kernel=kern,
-            device=self.device.index)
+            device=self.device.index, segments=_ptr(self._segments), n_segments=len(self._segments))
         h = C.c_void_p()
         check(lib.mfhn_op_create(C.byref(desc), C.byref(h)))
         self._h = h
@@ -291,8 +292,7 @@ class LaplaceOperator:
         check(lib.mfhn_op_set_apply_constraints(self._h, int(flag)))
 
     def set_kernel(self, kernel: str):
-        kern = {"auto": 0, "qpoint": 1, "separable": 2, "baseline": 3, "plane": 4}[kernel]
-        check(lib.mfhn_op_set_kernel(self._h, kern))
+        check(lib.mfhn_op_set_kernel(self._h, capi.KERNELS[kernel]))
 
     def query(self, what: str) -> float:
         v = C.c_double()

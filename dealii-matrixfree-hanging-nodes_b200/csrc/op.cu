@@ -6,6 +6,7 @@
 #include "fe1d.hpp"
 #include "kernels_generic.cuh"
 #include "kernels_plane.cuh"
+#include "kernels_patch.cuh"
 #include "octree.hpp"
 
 #include <cuda_runtime.h>
@@ -129,6 +130,113 @@ void PlaneLayout::build(int n_, int number, long long n_cells_, const uint32_t *
     }
 }
 
+template <int n, typename Number>
+static int patch_slot(int s, int j)
+{
+  using Cfg = PatchCfg<n, Number>;
+  return Cfg::slot(s, j % n, (j / n) % n, j / (n * n));
+}
+template <typename Number>
+static int patch_slot_n(int n, int s, int j)
+{
+  switch (n)
+    {
+      case 2: return patch_slot<2, Number>(s, j);
+      case 3: return patch_slot<3, Number>(s, j);
+      case 4: return patch_slot<4, Number>(s, j);
+      case 5: return patch_slot<5, Number>(s, j);
+      case 6: return patch_slot<6, Number>(s, j);
+      default: throw InvalidArgument("patch kernel not available for this degree");
+    }
+}
+
+void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *idx, const std::vector<long long> &segments)
+{
+  n      = n_;
+  number = number_;
+  const int cpw = 32 / n, P = 4 * cpw, n3 = n * n * n, ent_stride = P * n3;
+  // patches never straddle a segment boundary
+  patch_cell_begin.clear();
+  for (size_t sgm = 0; sgm < segments.size(); ++sgm)
+    {
+      const long long b = segments[sgm], e = sgm + 1 < segments.size() ? segments[sgm + 1] : n_cells;
+      for (long long c = b; c < e; c += P) patch_cell_begin.push_back(c);
+    }
+  n_patches = (long long)patch_cell_begin.size();
+  patch_cell_begin.push_back(n_cells);
+  std::vector<std::vector<uint32_t>> ulist(n_patches);
+  std::vector<std::vector<uint16_t>> olist(n_patches);
+  std::vector<uint16_t> ent((size_t)std::max<long long>(n_patches, 1) * ent_stride, 0);
+  std::vector<PatchInfo> info(std::max<long long>(n_patches, 1));
+#pragma omp parallel
+  {
+    std::vector<std::pair<uint32_t, uint16_t>> pairs;
+    struct Group { uint32_t g; int first, count; };
+    std::vector<Group> groups;
+#pragma omp for schedule(dynamic, 64)
+    for (long long pt = 0; pt < n_patches; ++pt)
+      {
+        const long long cb = patch_cell_begin[pt];
+        // a patch ends at the next patch start (segment ends are patch starts too)
+        const int nc = (int)std::min<long long>(P, patch_cell_begin[pt + 1] - cb);
+        pairs.clear();
+        for (int s = 0; s < nc; ++s)
+          for (int j = 0; j < n3; ++j)
+            {
+              const int slot = number == MFHN_F64 ? patch_slot_n<double>(n, s, j) : patch_slot_n<float>(n, s, j);
+              pairs.emplace_back(idx[(cb + s) * n3 + j], (uint16_t)slot);
+            }
+        std::sort(pairs.begin(), pairs.end());
+        groups.clear();
+        for (int i = 0; i < (int)pairs.size();)
+          {
+            int j = i;
+            while (j < (int)pairs.size() && pairs[j].first == pairs[i].first) ++j;
+            groups.push_back(Group{pairs[i].first, i, j - i});
+            i = j;
+          }
+        // uniform trip counts inside a warp: order by (multiplicity, address)
+        std::stable_sort(groups.begin(), groups.end(), [](const Group &a, const Group &b) { return a.count < b.count; });
+        auto &ul = ulist[pt];
+        auto &ol = olist[pt];
+        ul.resize(groups.size());
+        ol.resize(groups.size() + 1);
+        uint16_t *e = ent.data() + pt * ent_stride;
+        int pos     = 0;
+        for (size_t gi = 0; gi < groups.size(); ++gi)
+          {
+            ul[gi] = groups[gi].g;
+            ol[gi] = (uint16_t)pos;
+            for (int q = 0; q < groups[gi].count; ++q) e[pos++] = pairs[groups[gi].first + q].second;
+          }
+        ol[groups.size()] = (uint16_t)pos;
+        info[pt].cell_begin = cb;
+        info[pt].n_cells    = nc;
+        info[pt].n_unique   = (int)groups.size();
+      }
+  }
+  long long total = 0;
+  for (long long pt = 0; pt < n_patches; ++pt)
+    {
+      info[pt].uidx_start = total;
+      total += info[pt].n_unique;
+    }
+  std::vector<uint32_t> uidx((size_t)total + 1);
+  std::vector<uint16_t> off((size_t)total + n_patches + 1);
+#pragma omp parallel for schedule(static)
+  for (long long pt = 0; pt < n_patches; ++pt)
+    {
+      std::copy(ulist[pt].begin(), ulist[pt].end(), uidx.begin() + info[pt].uidx_start);
+      std::copy(olist[pt].begin(), olist[pt].end(), off.begin() + info[pt].uidx_start + pt);
+    }
+  unique_per_cell = n_cells > 0 ? (double)total / (double)n_cells : 0;
+  index_bytes     = total * 4 + (total + n_patches) * 2 + n_cells * (long long)n3 * 2 + n_patches * (long long)sizeof(PatchInfo);
+  d_patches       = to_device(info);
+  d_uidx          = to_device(uidx);
+  d_off           = to_device(off);
+  d_ent           = to_device(ent);
+}
+
 struct Operator
 {
   int degree = 0, number = 0, device = 0, geometry_type = 0;
@@ -138,6 +246,8 @@ struct Operator
   uint8_t *d_masks = nullptr;
   void *d_geom = nullptr;       // Number h[cell] or Number G[cell][6]
   PlaneLayout plane;            // warp-interleaved layout of the register-tiled kernel
+  PatchLayout patch;            // sorted-unique / CSR layout of the patch kernel
+  std::vector<long long> segments;
   long long launches = 0;
   void *d_stage_src = nullptr, *d_stage_dst = nullptr; // device staging of the host-buffer entry point
 
@@ -149,6 +259,7 @@ struct Operator
     cudaFree(d_stage_src);
     cudaFree(d_stage_dst);
     plane.free();
+    patch.free();
   }
 };
 
@@ -174,10 +285,10 @@ void launch_generic(const Operator &op, const CellLoopParams &p, cudaStream_t st
 template <int n, typename Number>
 void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
 {
-  if (kernel == MFHN_KERNEL_PLANE)
-    {
-      launch_plane<n, Number>(op.plane, p, op.device, stream);
-    }
+  if (kernel == MFHN_KERNEL_PATCH)
+    launch_patch<n, Number>(op.patch, p, op.device, stream);
+  else if (kernel == MFHN_KERNEL_PLANE)
+    launch_plane<n, Number>(op.plane, p, op.device, stream);
   else if (op.geometry_type == MFHN_GEOM_AFFINE)
     launch_generic<n, Number, GV_QPOINT_METRIC>(op, p, stream);
   else if (kernel == MFHN_KERNEL_SEPARABLE)
@@ -208,12 +319,15 @@ int resolve_kernel(const Operator &op)
 {
   int kernel = op.kernel;
   if (kernel == MFHN_KERNEL_AUTO)
-    kernel = (op.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(op.degree + 1)) ? MFHN_KERNEL_PLANE :
+    kernel = (op.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(op.degree + 1)) ? MFHN_KERNEL_PATCH :
              (op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_SEPARABLE : MFHN_KERNEL_QPOINT);
   if (op.geometry_type == MFHN_GEOM_AFFINE && kernel != MFHN_KERNEL_QPOINT)
     throw InvalidArgument("affine geometry requires MFHN_KERNEL_QPOINT");
-  if (kernel == MFHN_KERNEL_PLANE && !plane_supported(op.degree + 1))
-    throw NotImplemented("MFHN_KERNEL_PLANE is not available for this degree");
+  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH) && !plane_supported(op.degree + 1))
+    throw NotImplemented("MFHN_KERNEL_PLANE / MFHN_KERNEL_PATCH are not available for this degree");
+  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
+    throw InvalidArgument("this kernel requires Cartesian geometry");
+  if (kernel == MFHN_KERNEL_BASELINE) throw NotImplemented("MFHN_KERNEL_BASELINE is not built yet");
   return kernel;
 }
 
@@ -244,7 +358,7 @@ Operator *op_create(const mfhn_op_desc &d)
   if (d.n_cells < 0 || d.n_owned < 0 || d.n_ghost < 0) throw InvalidArgument("negative size");
   if (d.n_cells > 0 && (!d.dof_indices || !d.masks || !d.geometry)) throw InvalidArgument("null array");
   if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE) throw InvalidArgument("unknown geometry type");
-  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_PLANE) throw InvalidArgument("unknown kernel");
+  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_PATCH) throw InvalidArgument("unknown kernel");
   int device = d.device;
   if (device < 0)
     CUDA_CHECK(cudaGetDevice(&device));
@@ -309,6 +423,15 @@ Operator *op_create(const mfhn_op_desc &d)
     {
       const Shape1D sh = make_shape(d.degree);
       op->plane.build(n, d.number, d.n_cells, d.dof_indices, sh.W[0].data());
+      op->segments.assign(1, 0);
+      if (d.segments)
+        {
+          if (d.n_segments < 1 || d.segments[0] != 0) throw InvalidArgument("segments must start at cell 0");
+          op->segments.assign(d.segments, d.segments + d.n_segments);
+          for (int i = 1; i < d.n_segments; ++i)
+            if (d.segments[i] < d.segments[i - 1] || d.segments[i] > d.n_cells) throw InvalidArgument("segments must be ascending");
+        }
+      op->patch.build(n, d.number, d.n_cells, d.dof_indices, op->segments);
     }
   resolve_kernel(*op);
   return op.release();
@@ -462,7 +585,7 @@ int mfhn_op_set_kernel(mfhn_op h, int kernel)
     if (!h) throw InvalidArgument("null argument");
     Operator &op  = *reinterpret_cast<Operator *>(h);
     const int old = op.kernel;
-    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_PLANE) throw InvalidArgument("unknown kernel");
+    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_PATCH) throw InvalidArgument("unknown kernel");
     op.kernel = kernel;
     try
       {
@@ -501,8 +624,14 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
       *value = (double)op.n_cells_hn;
     else if (w == "algorithmic_bytes") // 2 s n_dofs + n_cells (4 (k+1)^3 + 1 + G)
       *value = 2 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : 10 * s));
+    else if (w == "algorithmic_bytes_accumulate") // + s n_dofs: dst is read as well when vmult accumulates
+      *value = 3 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : 10 * s));
     else if (w == "algorithmic_flops") // even-odd sum factorisation count of SURVEY 8d, without HN terms
       *value = (double)op.n_cells * (12 * n * n * (n * n + 2 * n) + 3 * n3);
+    else if (w == "unique_dofs_per_cell")
+      *value = op.patch.unique_per_cell;
+    else if (w == "patch_index_bytes")
+      *value = (double)op.patch.index_bytes;
     else if (w == "kernel")
       *value = (double)resolve_kernel(op);
     else

@@ -47,7 +47,8 @@ typedef struct mfhn_op_s *mfhn_op;
 #define MFHN_KERNEL_QPOINT 1    /* collocation sum factorisation + quadrature-point operation */
 #define MFHN_KERNEL_SEPARABLE 2 /* Cartesian cells only: 1D mass/stiffness tensor form        */
 #define MFHN_KERNEL_BASELINE 3  /* restatement of the deal.II CUDA design (one thread per DoF) */
-#define MFHN_KERNEL_PLANE 4     /* Cartesian cells, register-tiled separable kernel (fast path)  */
+#define MFHN_KERNEL_PLANE 4     /* Cartesian cells, register-tiled separable kernel, per-cell gather */
+#define MFHN_KERNEL_PATCH 5     /* same arithmetic, patch-wise sorted-unique gather/scatter (fast path) */
 
 const char *mfhn_last_error(void);
 const char *mfhn_version(void);
@@ -128,6 +129,10 @@ typedef struct
   int apply_constraints;       /* benchmark_03.h:255-268: false => plain gather/scatter        */
   int kernel;                  /* MFHN_KERNEL_*                                                */
   int device;                  /* CUDA device ordinal, -1 = current                            */
+  const int64_t *segments;     /* optional: ascending first cells of cell segments (segments[0]==0);
+                                  mfhn_op_vmult_range may only be called on unions of segments
+                                  (deal.II's cell_loop partitions for communication overlap)   */
+  int n_segments;
 } mfhn_op_desc;
 
 int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out);

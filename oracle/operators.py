@@ -94,6 +94,54 @@ def cell_laplace(u, h, degree):
     return r
 
 
+def vmult_abs_bound(lay, src, chunk=4096):
+    """|A| |src| evaluated through the same pipeline with every 1D matrix replaced by
+    its absolute value: the magnitude any floating-point evaluation of A src works
+    against (used to scale the single-precision parity check on smooth inputs,
+    where A src itself suffers cancellation)."""
+    n = lay.degree + 1
+    sd = fe1d.shape_data(lay.degree)
+    S, Dc, W, w = np.abs(sd.S), np.abs(sd.Dc), np.abs(sd.W), sd.qw
+    dst = np.zeros_like(src)
+    x = np.abs(src)
+    for c0 in range(0, lay.n_cells, chunk):
+        c1 = min(lay.n_cells, c0 + chunk)
+        idx = lay.dof_indices[c0:c1]
+        u = x[idx].reshape(-1, n, n, n)
+        kinds = lay.kinds[c0:c1]
+        for transpose in (False, True):
+            if transpose:
+                uq = np.einsum("qx,czyx->czyq", S, u)
+                uq = np.einsum("qy,czyx->czqx", S, uq)
+                uq = np.einsum("qz,czyx->cqyx", S, uq)
+                w3 = w[:, None, None] * w[None, :, None] * w[None, None, :]
+                fac = w3[None] * lay.h[c0:c1, None, None, None]
+                r = np.einsum("qx,czyq->czyx", Dc, np.einsum("qx,czyx->czyq", Dc, uq) * fac)
+                r += np.einsum("qy,czqx->czyx", Dc, np.einsum("qy,czyx->czqx", Dc, uq) * fac)
+                r += np.einsum("qz,cqyx->czyx", Dc, np.einsum("qz,czyx->cqyx", Dc, uq) * fac)
+                r = np.einsum("qz,cqyx->czyx", S, r)
+                r = np.einsum("qy,czqx->czyx", S, r)
+                u = np.einsum("qx,czyq->czyx", S, r)
+            for kind in np.unique(kinds):
+                kind = int(kind)
+                if kind == 0:
+                    continue
+                cells = np.nonzero(kinds == kind)[0]
+                v = u[cells]
+                for d in range(3):
+                    sel = hn_selection(kind, d, lay.degree)
+                    if not sel.any():
+                        continue
+                    s = 1 - ((kind >> d) & 1)
+                    Wm = W[s].T if transpose else W[s]
+                    vm = np.moveaxis(v, 3 - d, -1)
+                    new = vm @ Wm.T
+                    vm[:, sel, :] = new[:, sel, :]
+                u[cells] = v
+        np.add.at(dst, idx.ravel(), u.ravel())
+    return dst
+
+
 def vmult_fast(lay, src, apply_constraints=True, dst=None, chunk=4096):
     """dst += A src with the fast algorithm (accumulating like
     benchmark_03.h:237-241)."""
