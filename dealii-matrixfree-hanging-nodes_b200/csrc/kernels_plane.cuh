@@ -187,83 +187,48 @@ __device__ __forceinline__ void apply_Mb_Ka(const Number (&a)[n], const Number (
     }
 }
 
-// ---- hanging-node interpolation on thread-owned (x,y) planes ----------------
-// u[y][x] is the plane z = t of the cell; the n threads of a cell sit in lanes
-// base .. base+n-1.  x and y passes stay in registers, the z pass exchanges the
-// ring values (x or y on the cell boundary) with warp shuffles.
+// In-place hanging-node interpolation (or its transpose) on the cell arrays of
+// one warp: three directional passes, every thread of a cell takes n of the
+// n^2 lines of a pass.
 template <int n, bool transpose, typename Number>
-__device__ __forceinline__ void hn_plane(Number (&u)[n][n], unsigned mask, int t, int base, const Number *__restrict__ w0)
+__device__ __forceinline__ void hn_smem(Number *cellA, unsigned mask, int t)
 {
   constexpr int k = n - 1;
+  using Cfg = PlaneCfg<n, Number>;
   unsigned face, edge, cb;
   decode_mask(mask, face, edge, cb);
-  const bool fx = face & 1u, fy = face & 2u, fz = face & 4u;
-  const bool ex = edge & 1u, ey = edge & 2u, ez = edge & 4u;
-  const bool upx = cb & 1u, upy = cb & 2u, upz = cb & 4u;
-  const int X0 = upx ? k : 0, Y0 = upy ? k : 0, Z0 = upz ? k : 0;
-  const bool onz = (t == Z0);
-  const bool planez = fz && onz; // the whole plane lies on the constrained z face
-  // pass x: lines along x, one per y
-#pragma unroll
-  for (int y = 0; y < n; ++y)
+#pragma unroll 1
+  for (int d = 0; d < 3; ++d)
     {
-      const bool sel = planez || ((y == Y0) && (fy || (ex && onz)));
-      if (sel)
+      const int t0 = (d == 0) ? 1 : 0, t1 = (d == 2) ? 1 : 2;
+      const int c0 = (int)((cb >> t0) & 1u) * k, c1 = (int)((cb >> t1) & 1u) * k;
+      const bool f0 = (face >> t0) & 1u, f1 = (face >> t1) & 1u, ed = (edge >> d) & 1u;
+      const bool upper = (cb >> d) & 1u;
+      const int stride = d == 0 ? 1 : d == 1 ? n : Cfg::ps;
+      const int b      = t;
+#pragma unroll 1
+      for (int a = 0; a < n; ++a)
         {
-          Number v[n], w[n];
-#pragma unroll
-          for (int i = 0; i < n; ++i) v[i] = upx ? u[y][k - i] : u[y][i];
-          mat_vec<n, T_W0, transpose>(v, w);
-#pragma unroll
-          for (int i = 0; i < n; ++i)
+          const bool on0 = a == c0, on1 = b == c1;
+          const bool sel = mask != 0u && ((f0 && on0) || (f1 && on1) || (ed && on0 && on1));
+          if (sel)
             {
-              u[y][i] = upx ? w[k - i] : w[i];
+              const int base = d == 0 ? b * Cfg::ps + a * n : d == 1 ? b * Cfg::ps + a : b * n + a;
+              Number *line   = cellA + base;
+              Number v[n], w[n];
+#pragma unroll
+              for (int i = 0; i < n; ++i) v[i] = line[(upper ? k - i : i) * stride];
+              mat_vec<n, T_W0, transpose>(v, w);
+#pragma unroll
+              for (int i = 0; i < n; ++i) line[(upper ? k - i : i) * stride] = w[i];
             }
         }
+      __syncwarp();
     }
-  // pass y: lines along y, one per x
-#pragma unroll
-  for (int x = 0; x < n; ++x)
-    {
-      const bool sel = planez || ((x == X0) && (fx || (ey && onz)));
-      if (sel)
-        {
-          Number v[n], w[n];
-#pragma unroll
-          for (int i = 0; i < n; ++i) v[i] = upy ? u[k - i][x] : u[i][x];
-          mat_vec<n, T_W0, transpose>(v, w);
-#pragma unroll
-          for (int i = 0; i < n; ++i) u[i][x] = upy ? w[k - i] : w[i];
-        }
-    }
-  // pass z: lines along z through ring positions, exchanged by shuffles
-  Number wz[n];
-#pragma unroll
-  for (int zz = 0; zz < n; ++zz)
-    {
-      // forward: W_bz[t][zz];  transpose: W_bz[zz][t];  W_1[i][j] = W_0[k-i][k-j]
-      const int i = transpose ? zz : t, j = transpose ? t : zz;
-      wz[zz]      = w0[upz ? (k - i) * n + (k - j) : i * n + j];
-    }
-#pragma unroll
-  for (int y = 0; y < n; ++y)
-#pragma unroll
-    for (int x = 0; x < n; ++x)
-      {
-        if (!(x == 0 || x == k || y == 0 || y == k)) continue;
-        const bool sel = ((x == X0) && fx) || ((y == Y0) && fy) || (ez && x == X0 && y == Y0);
-        if (__any_sync(0xffffffffu, sel))
-          {
-            Number acc = Number(0);
-#pragma unroll
-            for (int zz = 0; zz < n; ++zz) acc += wz[zz] * __shfl_sync(0xffffffffu, u[y][x], base + zz);
-            if (sel) u[y][x] = acc;
-          }
-      }
 }
 
 template <int n, typename Number>
-__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32) plane_cell_kernel(const PlaneParams p)
+__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell_kernel(const PlaneParams p)
 {
   using Cfg = PlaneCfg<n, Number>;
   constexpr int ps = Cfg::ps, cs = Cfg::cs;
@@ -274,29 +239,42 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32) plane_cell_ke
   Number *A = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * 2 * Cfg::cpw * cs;
   Number *B = A + Cfg::cpw * cs;
 
-  const int c = lane / n, t = lane - c * n;
+  // the 32 - cpw n idle lanes mirror lane 0 (same loads, same values stored to the same
+  // shared-memory addresses), so the arithmetic needs no per-lane predicate; they do not scatter
   const bool active = lane < Cfg::lanes;
+  const int c = active ? lane / n : 0, t = active ? lane - c * n : 0;
   const long long cell = batch * Cfg::cpw + c;
-  const bool valid = active && cell >= p.cell_begin && cell < p.cell_end;
+  const bool valid = cell >= p.cell_begin && cell < p.cell_end;
   const Number *__restrict__ src = static_cast<const Number *>(p.src);
   Number *__restrict__ dst = static_cast<Number *>(p.dst);
+  const uint32_t *ip = p.pidx + batch * (long long)(n * n * 32) + (c * n + t);
+  Number *cellA = A + c * cs, *cellB = B + c * cs;
 
-  // ---- P1: gather ------------------------------------------------------------
-  uint32_t idx[n * n];
+  // ---- P1: gather (thread = z, plane (x,y)) ---------------------------------------
+  Number u[n][n];
   {
-    const uint32_t *ip = p.pidx + batch * (long long)(n * n * 32) + lane;
+    uint32_t idx[n * n];
 #pragma unroll
     for (int j = 0; j < n * n; ++j) idx[j] = valid ? __ldg(ip + j * 32) : 0xffffffffu;
-  }
-  Number u[n][n];
 #pragma unroll
-  for (int j = 0; j < n * n; ++j) u[j / n][j % n] = (idx[j] != 0xffffffffu) ? __ldg(src + idx[j]) : Number(0);
+    for (int j = 0; j < n * n; ++j) u[j / n][j % n] = (idx[j] != 0xffffffffu) ? __ldg(src + idx[j]) : Number(0);
+  }
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
   const bool any_hn   = __any_sync(0xffffffffu, mask != 0u);
-  if (any_hn) hn_plane<n, false>(u, mask, t, lane - t, static_cast<const Number *>(p.w0));
+  if (any_hn)
+    {
+      // hanging-node interpolation as in-place directional passes on the shared-memory copy
+#pragma unroll
+      for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+      __syncwarp();
+      hn_smem<n, false>(cellA, mask, t);
+#pragma unroll
+      for (int j = 0; j < n * n; ++j) u[j / n][j % n] = cellA[t * ps + j];
+      __syncwarp();
+    }
 
-  // ---- P1: x and y sweeps ------------------------------------------------------
+  // ---- P1: x and y sweeps ------------------------------------------------------------
   {
     Number pp[n][n], qq[n][n];
 #pragma unroll
@@ -312,47 +290,42 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32) plane_cell_ke
             qc[i] = qq[i][x];
           }
         apply_M_MK<n>(pc, qc, a, b);
-        if (active)
-          {
 #pragma unroll
-            for (int i = 0; i < n; ++i)
-              {
-                A[c * cs + t * ps + i * n + x] = a[i];
-                B[c * cs + t * ps + i * n + x] = b[i];
-              }
+        for (int i = 0; i < n; ++i)
+          {
+            cellA[t * ps + i * n + x] = a[i];
+            cellB[t * ps + i * n + x] = b[i];
           }
       }
   }
   __syncwarp();
-  // ---- P2: z sweep (thread = x) ----------------------------------------------
-  if (active)
+  // ---- P2: z sweep (thread = x) ------------------------------------------------------
+#pragma unroll
+  for (int y = 0; y < n; ++y)
     {
+      Number a[n], b[n], r[n];
 #pragma unroll
-      for (int y = 0; y < n; ++y)
+      for (int z = 0; z < n; ++z)
         {
-          Number a[n], b[n], r[n];
-#pragma unroll
-          for (int z = 0; z < n; ++z)
-            {
-              a[z] = A[c * cs + z * ps + y * n + t];
-              b[z] = B[c * cs + z * ps + y * n + t];
-            }
-          apply_Mb_Ka<n>(a, b, r);
-#pragma unroll
-          for (int z = 0; z < n; ++z) A[c * cs + z * ps + y * n + t] = h * r[z];
+          a[z] = cellA[z * ps + y * n + t];
+          b[z] = cellB[z * ps + y * n + t];
         }
+      apply_Mb_Ka<n>(a, b, r);
+#pragma unroll
+      for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
     }
   __syncwarp();
-  // ---- P3: interpolation^T and scatter (thread = z) --------------------------
-  if (active)
+  if (any_hn) hn_smem<n, true>(cellA, mask, t);
+  // ---- P3: scatter (thread = z) --------------------------------------------------------
+  if (active && valid)
     {
 #pragma unroll
-      for (int j = 0; j < n * n; ++j) u[j / n][j % n] = A[c * cs + t * ps + j];
+      for (int j = 0; j < n * n; ++j)
+        {
+          const uint32_t g = __ldg(ip + j * 32);
+          if (g != 0xffffffffu) atomicAdd(dst + g, cellA[t * ps + j]);
+        }
     }
-  if (any_hn) hn_plane<n, true>(u, mask, t, lane - t, static_cast<const Number *>(p.w0));
-#pragma unroll
-  for (int j = 0; j < n * n; ++j)
-    if (idx[j] != 0xffffffffu) atomicAdd(dst + idx[j], u[j / n][j % n]);
 }
 
 // ---- host side ------------------------------------------------------------------

@@ -154,7 +154,7 @@ void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *
 {
   n      = n_;
   number = number_;
-  const int cpw = 32 / n, P = 4 * cpw, n3 = n * n * n, ent_stride = P * n3;
+  const int cpw = 32 / n, P = cpw, n3 = n * n * n, ent_stride = P * n3;
   // patches never straddle a segment boundary
   patch_cell_begin.clear();
   for (size_t sgm = 0; sgm < segments.size(); ++sgm)
@@ -164,11 +164,11 @@ void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *
     }
   n_patches = (long long)patch_cell_begin.size();
   patch_cell_begin.push_back(n_cells);
-  std::vector<std::vector<uint32_t>> ulist(n_patches);
-  std::vector<std::vector<uint16_t>> olist(n_patches);
+  std::vector<uint32_t> uidx((size_t)std::max<long long>(n_patches, 1) * ent_stride, 0u);
   std::vector<uint16_t> ent((size_t)std::max<long long>(n_patches, 1) * ent_stride, 0);
   std::vector<PatchInfo> info(std::max<long long>(n_patches, 1));
-#pragma omp parallel
+  long long total = 0;
+#pragma omp parallel reduction(+ : total)
   {
     std::vector<std::pair<uint32_t, uint16_t>> pairs;
     struct Group { uint32_t g; int first, count; };
@@ -192,48 +192,47 @@ void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *
           {
             int j = i;
             while (j < (int)pairs.size() && pairs[j].first == pairs[i].first) ++j;
-            groups.push_back(Group{pairs[i].first, i, j - i});
+            // multiplicities other than 1, 2, 4, 8 are split (3 = 2 + 1, ...): such a DoF is
+            // listed more than once, i.e. read twice and sent two REDs
+            int first = i, left = j - i;
+            while (left > 0)
+              {
+                const int piece = left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
+                groups.push_back(Group{pairs[i].first, first, piece});
+                first += piece;
+                left -= piece;
+              }
             i = j;
           }
-        // uniform trip counts inside a warp: order by (multiplicity, address)
+        // classes by multiplicity (uniform trip counts), ascending address inside a class
         std::stable_sort(groups.begin(), groups.end(), [](const Group &a, const Group &b) { return a.count < b.count; });
-        auto &ul = ulist[pt];
-        auto &ol = olist[pt];
-        ul.resize(groups.size());
-        ol.resize(groups.size() + 1);
+        PatchInfo &pi = info[pt];
+        pi.cell_begin = cb;
+        pi.n_cells    = nc;
+        pi.pad[0] = pi.pad[1] = pi.pad[2] = 0;
+        for (int m = 0; m < N_CLASSES; ++m) pi.count[m] = 0;
+        for (const Group &g : groups) ++pi.count[g.count == 1 ? 0 : g.count == 2 ? 1 : g.count == 4 ? 2 : 3];
+        uint32_t *u = uidx.data() + pt * ent_stride;
         uint16_t *e = ent.data() + pt * ent_stride;
-        int pos     = 0;
-        for (size_t gi = 0; gi < groups.size(); ++gi)
+        size_t gi = 0;
+        int ebase = 0;
+        for (int ci = 0; ci < N_CLASSES; ++ci)
           {
-            ul[gi] = groups[gi].g;
-            ol[gi] = (uint16_t)pos;
-            for (int q = 0; q < groups[gi].count; ++q) e[pos++] = pairs[groups[gi].first + q].second;
+            const int m = 1 << ci, cnt = pi.count[ci];
+            for (int i = 0; i < cnt; ++i, ++gi)
+              {
+                u[gi] = groups[gi].g;
+                for (int q = 0; q < m; ++q) e[ebase + q * cnt + i] = pairs[groups[gi].first + q].second;
+              }
+            ebase += m * cnt;
           }
-        ol[groups.size()] = (uint16_t)pos;
-        info[pt].cell_begin = cb;
-        info[pt].n_cells    = nc;
-        info[pt].n_unique   = (int)groups.size();
+        total += (long long)groups.size();
       }
   }
-  long long total = 0;
-  for (long long pt = 0; pt < n_patches; ++pt)
-    {
-      info[pt].uidx_start = total;
-      total += info[pt].n_unique;
-    }
-  std::vector<uint32_t> uidx((size_t)total + 1);
-  std::vector<uint16_t> off((size_t)total + n_patches + 1);
-#pragma omp parallel for schedule(static)
-  for (long long pt = 0; pt < n_patches; ++pt)
-    {
-      std::copy(ulist[pt].begin(), ulist[pt].end(), uidx.begin() + info[pt].uidx_start);
-      std::copy(olist[pt].begin(), olist[pt].end(), off.begin() + info[pt].uidx_start + pt);
-    }
   unique_per_cell = n_cells > 0 ? (double)total / (double)n_cells : 0;
-  index_bytes     = total * 4 + (total + n_patches) * 2 + n_cells * (long long)n3 * 2 + n_patches * (long long)sizeof(PatchInfo);
+  index_bytes     = total * 4 + n_cells * (long long)n3 * 2 + n_patches * (long long)sizeof(PatchInfo);
   d_patches       = to_device(info);
   d_uidx          = to_device(uidx);
-  d_off           = to_device(off);
   d_ent           = to_device(ent);
 }
 
