@@ -185,6 +185,8 @@ class MatrixFree:
         touches = is_ghost.reshape(sub.shape).any(axis=1)
         order = np.concatenate([np.nonzero(~touches)[0], np.nonzero(touches)[0]])
         self.n_interior_cells = int((~touches).sum())
+        # deal.II's cell_loop overlaps the two ghost exchanges with two interior partitions
+        self.n_interior_a = self.n_interior_cells // 2 if dh.n_ranks > 1 else self.n_interior_cells
         self.cell_ids = cells[order]
         self.dof_indices = np.ascontiguousarray(local[order].astype(np.uint32))
         self.masks = np.ascontiguousarray(masks[order])
@@ -239,8 +241,8 @@ class LaplaceOperator:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         part = matrix_free.partitioner
         kern = capi.KERNELS[kernel]
-        ni = matrix_free.n_interior_cells
-        self._segments = np.array([0, ni] if 0 < ni < matrix_free.n_cells else [0], dtype=np.int64)
+        cuts = sorted({0, matrix_free.n_interior_a, matrix_free.n_interior_cells} - {matrix_free.n_cells})
+        self._segments = np.array(cuts, dtype=np.int64)
         if geometry is None:
             gtype, geom = capi.GEOM_CARTESIAN, matrix_free.h
         else:  # (n_cells, 3, 3) Jacobians

@@ -1,0 +1,148 @@
+"""Ghost exchange of the partitioned operator: the device side of
+LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) as
+CUDAWrappers::MatrixFree::cell_loop uses them (reference: benchmark_03.h:348-353
+with the distributed vectors of :323-324; deal.II interleaves the two exchanges
+with three cell partitions).
+
+One process per GPU; torch.distributed (NCCL over NVLink, gloo in the CPU
+tests) carries the messages, this package's own kernels pack / unpack on the
+GPU.  Schedule of one vmult (compute stream || communication stream):
+
+    pack imports            |
+    interior cells, part A  |  owners -> ghosts   (update_ghost_values)
+    boundary cells          |
+    interior cells, part B  |  ghosts -> owners   (compress, part 1)
+    unpack-add, zero ghosts |
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import check, lib
+
+
+class GhostExchange:
+    """Owns the send/receive buffers and index lists of one rank.
+
+    local_apply(dst, src, cell_begin, cell_end) applies the rank-local cell
+    loop on a cell range; by default the CUDA operator's vmult_range.  The CPU
+    tests pass the oracle here to exercise the exchange logic under gloo."""
+
+    def __init__(self, op=None, partitioner=None, segments=None, local_apply=None, device=None, dtype=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.op = op
+        part = partitioner if partitioner is not None else op.mf.partitioner
+        self.part = part
+        self.device = device if device is not None else op.device
+        self.dtype = dtype if dtype is not None else op.dtype
+        self.number = capi.F64 if self.dtype == torch.float64 else capi.F32
+        self.cuda = torch.device(self.device).type == "cuda"
+        self.local_apply = local_apply if local_apply is not None else op.vmult_range
+        # cell segments [interior A | interior B | boundary]
+        if segments is None:
+            mf = op.mf
+            segments = (0, mf.n_interior_a, mf.n_interior_cells, mf.n_cells)
+        self.seg = tuple(int(s) for s in segments)
+        self.n_owned, self.n_ghost = part.n_owned, part.n_ghost
+        self.import_peers = sorted(part.import_indices)
+        self.ghost_peers = sorted(part.ghost_ranges)
+        self.import_idx = {p: torch.from_numpy(np.ascontiguousarray(part.import_indices[p], dtype=np.int32)).to(self.device)
+                           for p in self.import_peers}
+        self.send_buf = {p: torch.empty(len(part.import_indices[p]), dtype=self.dtype, device=self.device) for p in self.import_peers}
+        self.recv_buf = {p: torch.empty(len(part.import_indices[p]), dtype=self.dtype, device=self.device) for p in self.import_peers}
+        if self.cuda:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.n_launches = 0
+
+    # -- building blocks ---------------------------------------------------------
+    def _global_rank(self, p):
+        return p if self.group is None else self.dist.get_global_rank(self.group, p)
+
+    def _pack(self, vec):
+        for p in self.import_peers:
+            idx, buf = self.import_idx[p], self.send_buf[p]
+            if self.cuda:
+                stream = self.torch.cuda.current_stream(self.device).cuda_stream
+                check(lib.mfhn_pack(self.number, buf.data_ptr(), vec.data_ptr(), idx.data_ptr(), idx.numel(), stream))
+                self.n_launches += 1
+            else:
+                buf.copy_(vec[idx.long()])
+
+    def _unpack_add(self, vec):
+        for p in self.import_peers:
+            idx, buf = self.import_idx[p], self.recv_buf[p]
+            if self.cuda:
+                stream = self.torch.cuda.current_stream(self.device).cuda_stream
+                check(lib.mfhn_unpack_add(self.number, vec.data_ptr(), buf.data_ptr(), idx.data_ptr(), idx.numel(), stream))
+                self.n_launches += 1
+            else:
+                vec.index_add_(0, idx.long(), buf)
+
+    def _exchange(self, sends, recvs):
+        """sends / recvs: lists of (tensor, peer).  Grouped non-blocking p2p."""
+        dist = self.dist
+        ops = [dist.P2POp(dist.irecv, t, self._global_rank(p), group=self.group) for t, p in recvs]
+        ops += [dist.P2POp(dist.isend, t, self._global_rank(p), group=self.group) for t, p in sends]
+        if not ops:
+            return
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def _ghost_view(self, vec, p):
+        a, b = self.part.ghost_ranges[p]
+        return vec[self.n_owned + a:self.n_owned + b]
+
+    # -- LinearAlgebra::distributed::Vector interface --------------------------------
+    def update_ghost_values(self, vec):
+        self._pack(vec)
+        self._exchange([(self.send_buf[p], p) for p in self.import_peers], [(self._ghost_view(vec, p), p) for p in self.ghost_peers])
+
+    def compress_add(self, vec):
+        self._exchange([(self._ghost_view(vec, p), p) for p in self.ghost_peers], [(self.recv_buf[p], p) for p in self.import_peers])
+        self._unpack_add(vec)
+        vec[self.n_owned:].zero_()
+
+    def zero_out_ghost_values(self, vec):
+        vec[self.n_owned:].zero_()
+
+    # -- the overlapped cell loop -------------------------------------------------------
+    def vmult(self, op, dst, src, zero_dst=False):
+        torch = self.torch
+        s0, s1, s2, s3 = self.seg
+        if zero_dst:
+            dst.zero_()
+        if not self.cuda:
+            self.update_ghost_values(src)
+            self.local_apply(dst, src, s0, s3)
+            self.compress_add(dst)
+            return
+        main = torch.cuda.current_stream(self.device)
+        comm = self.comm_stream
+        self._pack(src)
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            self._exchange([(self.send_buf[p], p) for p in self.import_peers], [(self._ghost_view(src, p), p) for p in self.ghost_peers])
+        if s1 > s0:
+            self.local_apply(dst, src, s0, s1)  # interior A overlaps the import
+            self.n_launches += 1
+        main.wait_stream(comm)
+        if s3 > s2:
+            self.local_apply(dst, src, s2, s3)  # boundary cells need the ghosts
+            self.n_launches += 1
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            self._exchange([(self._ghost_view(dst, p), p) for p in self.ghost_peers], [(self.recv_buf[p], p) for p in self.import_peers])
+        if s2 > s1:
+            self.local_apply(dst, src, s1, s2)  # interior B overlaps the compress
+            self.n_launches += 1
+        main.wait_stream(comm)
+        self._unpack_add(dst)
+        dst[self.n_owned:].zero_()
+
+    def launches_per_vmult(self):
+        s0, s1, s2, s3 = self.seg
+        return int(s1 > s0) + int(s2 > s1) + int(s3 > s2) + 2 * len(self.import_peers)
