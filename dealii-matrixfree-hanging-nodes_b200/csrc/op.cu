@@ -318,7 +318,7 @@ int resolve_kernel(const Operator &op)
 {
   int kernel = op.kernel;
   if (kernel == MFHN_KERNEL_AUTO)
-    kernel = (op.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(op.degree + 1)) ? MFHN_KERNEL_PATCH :
+    kernel = (op.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(op.degree + 1)) ? MFHN_KERNEL_PLANE :
              (op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_SEPARABLE : MFHN_KERNEL_QPOINT);
   if (op.geometry_type == MFHN_GEOM_AFFINE && kernel != MFHN_KERNEL_QPOINT)
     throw InvalidArgument("affine geometry requires MFHN_KERNEL_QPOINT");

@@ -201,3 +201,23 @@ def test_error_behaviour(mfhn):
     v = op.initialize_dof_vector()
     with pytest.raises(mfhn.MfhnError):
         op.vmult(v, v)
+
+
+def test_cpp_driver_over_c_abi(mfhn):
+    """examples/benchmark_03 (C++ host code over the C ABI, laid out like the reference's
+    benchmark_03 run()) reproduces the oracle's |A src|_2 for src = sum sin x_d."""
+    import os
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "benchmark_03")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    out = subprocess.run([exe, "annulus", "3", "5", "5"], check=True, capture_output=True, text=True).stdout
+    got = float(re.search(r"n_repetitions = ([0-9.e+-]+)", out).group(1))
+    lay = dofs.setup(mesh.create("annulus", 5, "p4est"), 3)
+    ref = np.linalg.norm(operators.vmult_fast(lay, np.sin(lay.support_points).sum(axis=1)))
+    assert abs(got - ref) / ref < 1e-10
+    cols = out.splitlines()[1].split()
+    assert int(cols[3]) == lay.n_cells and int(cols[5]) == lay.n_dofs and int(cols[4]) == int((lay.masks != 0).sum())
