@@ -230,9 +230,11 @@ __global__ void __launch_bounds__(PatchCfg<n, Number>::warps * 32, 3) patch_cell
     const unsigned mask  = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
     const Number h       = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
     const bool any_hn    = __any_sync(0xffffffffu, mask != 0u);
+    unsigned hn_face, hn_edge, hn_cb;
+    decode_mask(mask, hn_face, hn_edge, hn_cb); // the patch layout keeps physical axes
     Number *cellA        = A + c * cs;
     Number *cellB        = B + c * cs;
-    if (any_hn) hn_smem<n, false>(cellA, mask, t);
+    if (any_hn) hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t);
 
     // P1 (thread = z): plane (x,y) -> a = M_y M_x u, b = (M_y K_x + K_y M_x) u
     Number u[n][n];
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(PatchCfg<n, Number>::warps * 32, 3) patch_cell
         for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
       }
     __syncwarp();
-    if (any_hn) hn_smem<n, true>(cellA, mask, t);
+    if (any_hn) hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t);
   }
   __syncwarp();
 

@@ -4,9 +4,9 @@
 // per batch of cells; a warp never synchronises with another warp.  Each
 // thread owns one n x n plane of the cell's n^3 values in registers:
 //
-//   P1 (thread = z, plane (x,y)):  gather -> hanging-node interpolation
-//        (x, y passes in registers, z pass by warp shuffles) ->
-//        a = M_y M_x u,  b = (M_y K_x + K_y M_x) u          -> shared memory
+//   P1 (thread = z, plane (x,y)):  gather -> [hanging-node interpolation: in-place
+//        directional passes on a shared-memory copy, only in warps with a
+//        constrained cell] -> a = M_y M_x u,  b = (M_y K_x + K_y M_x) u  -> shared memory
 //   P2 (thread = x, plane (y,z)):  r = h (M_z b + K_z a)      -> shared memory
 //   P3 (thread = z, plane (x,y)):  interpolation^T -> atomic scatter-add
 //
@@ -18,7 +18,10 @@
 // M and K are persymmetric, so every sweep uses the even-odd decomposition.
 //
 // The DoF indices are stored warp-interleaved ([batch][plane slot][lane]) so
-// that every index load is one coalesced 128-byte request.
+// that every index load is one coalesced 128-byte request.  The kernel's thread
+// axis Z is the physical x direction (kernel axes (X,Y,Z) = physical (y,z,x)):
+// the threads of a cell then read consecutive x, the most contiguous direction
+// of deal.II's object-wise DoF numbering (fewer 128-byte lines per request).
 #pragma once
 #include "kernels_generic.cuh"
 #include "shape_tables.cuh"
@@ -188,43 +191,62 @@ __device__ __forceinline__ void apply_Mb_Ka(const Number (&a)[n], const Number (
 }
 
 // In-place hanging-node interpolation (or its transpose) on the cell arrays of
-// one warp: three directional passes, every thread of a cell takes n of the
-// n^2 lines of a pass.
+// one warp: three directional passes over kernel axes (X,Y,Z) = shared-memory
+// strides (1, n, ps).  face / edge / cb are the constraint bits already permuted
+// to kernel axes.  In a pass the n^2 lines are shared by the n threads of the
+// cell; the assignment is chosen per cell so that the lines of a constrained
+// face land on n different threads of the same iteration.
 template <int n, bool transpose, typename Number>
-__device__ __forceinline__ void hn_smem(Number *cellA, unsigned mask, int t)
+__device__ __forceinline__ void hn_smem(Number *cellA, unsigned face, unsigned edge, unsigned cb, int t)
 {
   constexpr int k = n - 1;
   using Cfg = PlaneCfg<n, Number>;
-  unsigned face, edge, cb;
-  decode_mask(mask, face, edge, cb);
 #pragma unroll 1
   for (int d = 0; d < 3; ++d)
     {
       const int t0 = (d == 0) ? 1 : 0, t1 = (d == 2) ? 1 : 2;
       const int c0 = (int)((cb >> t0) & 1u) * k, c1 = (int)((cb >> t1) & 1u) * k;
       const bool f0 = (face >> t0) & 1u, f1 = (face >> t1) & 1u, ed = (edge >> d) & 1u;
+      const bool work = f0 || f1 || ed;
       const bool upper = (cb >> d) & 1u;
       const int stride = d == 0 ? 1 : d == 1 ? n : Cfg::ps;
-      const int b      = t;
+      // f1 (lines b == c1, all a): thread = a, iteration = b; otherwise thread = b, iteration = a
+      const int last = !work ? 0 : (f0 && f1) ? n : 1; // a single face / edge needs one iteration
+      const int first = f1 ? c1 : c0;
 #pragma unroll 1
-      for (int a = 0; a < n; ++a)
+      for (int it = 0; it < last; ++it)
         {
+          const int i = (first + it) % n; // start with the iteration that holds the whole face
+          const int a = f1 ? t : i, b = f1 ? i : t;
           const bool on0 = a == c0, on1 = b == c1;
-          const bool sel = mask != 0u && ((f0 && on0) || (f1 && on1) || (ed && on0 && on1));
+          const bool sel = (f0 && on0) || (f1 && on1) || (ed && on0 && on1);
           if (sel)
             {
               const int base = d == 0 ? b * Cfg::ps + a * n : d == 1 ? b * Cfg::ps + a : b * n + a;
               Number *line   = cellA + base;
               Number v[n], w[n];
 #pragma unroll
-              for (int i = 0; i < n; ++i) v[i] = line[(upper ? k - i : i) * stride];
+              for (int i2 = 0; i2 < n; ++i2) v[i2] = line[(upper ? k - i2 : i2) * stride];
               mat_vec<n, T_W0, transpose>(v, w);
 #pragma unroll
-              for (int i = 0; i < n; ++i) line[(upper ? k - i : i) * stride] = w[i];
+              for (int i2 = 0; i2 < n; ++i2) line[(upper ? k - i2 : i2) * stride] = w[i2];
             }
         }
-      __syncwarp();
+      __syncwarp(); // the next pass reads lines written by other threads
     }
+}
+
+// Constraint bits of a compressed mask in KERNEL axes.  The plane / patch kernels
+// use x as the thread axis (threads of a cell read consecutive x: the most
+// contiguous direction of deal.II's object-wise numbering), i.e. kernel axes
+// (X,Y,Z) = physical (y,z,x).
+__device__ __forceinline__ unsigned rot3(unsigned b) { return ((b >> 1) | (b << 2)) & 7u; }
+__device__ __forceinline__ void decode_mask_kernel_axes(unsigned m, unsigned &face, unsigned &edge, unsigned &cb)
+{
+  decode_mask(m, face, edge, cb);
+  face = rot3(face);
+  edge = rot3(edge);
+  cb   = rot3(cb);
 }
 
 template <int n, typename Number>
@@ -262,13 +284,15 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
   const bool any_hn   = __any_sync(0xffffffffu, mask != 0u);
+  unsigned hn_face, hn_edge, hn_cb;
+  decode_mask_kernel_axes(mask, hn_face, hn_edge, hn_cb);
   if (any_hn)
     {
       // hanging-node interpolation as in-place directional passes on the shared-memory copy
 #pragma unroll
       for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
       __syncwarp();
-      hn_smem<n, false>(cellA, mask, t);
+      hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t);
 #pragma unroll
       for (int j = 0; j < n * n; ++j) u[j / n][j % n] = cellA[t * ps + j];
       __syncwarp();
@@ -315,7 +339,7 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell
       for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
     }
   __syncwarp();
-  if (any_hn) hn_smem<n, true>(cellA, mask, t);
+  if (any_hn) hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t);
   // ---- P3: scatter (thread = z) --------------------------------------------------------
   if (active && valid)
     {

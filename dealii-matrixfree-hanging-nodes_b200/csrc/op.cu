@@ -114,8 +114,9 @@ void PlaneLayout::build(int n_, int number, long long n_cells_, const uint32_t *
     {
       const long long batch = c / cpw;
       const int slot        = (int)(c % cpw);
+      // kernel axes (X,Y,Z) = physical (y,z,x): thread t = x, plane slot j = y + n z
       for (int t = 0; t < n; ++t)
-        for (int j = 0; j < n2; ++j) p[((size_t)batch * n2 + j) * 32 + slot * n + t] = idx[c * n3 + j + (long long)n2 * t];
+        for (int j = 0; j < n2; ++j) p[((size_t)batch * n2 + j) * 32 + slot * n + t] = idx[c * n3 + t + (long long)n * j];
     }
   d_pidx = to_device(p);
   if (number == MFHN_F64)
