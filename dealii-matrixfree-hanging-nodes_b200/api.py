@@ -163,7 +163,7 @@ class MatrixFree:
     cell order (Morton, interior cells first), rank-local substituted DoF
     indices, compressed masks, Cartesian geometry and the ghost partitioner."""
 
-    def __init__(self, dof_handler: DoFHandler, rank: int = 0):
+    def __init__(self, dof_handler: DoFHandler, rank: int = 0, categorize: bool = True):
         self.dof_handler, self.rank = dof_handler, rank
         dh = dof_handler
         self.degree = dh.degree
@@ -185,6 +185,16 @@ class MatrixFree:
         touches = is_ghost.reshape(sub.shape).any(axis=1)
         order = np.concatenate([np.nonzero(~touches)[0], np.nonzero(touches)[0]])
         self.n_interior_cells = int((~touches).sum())
+        if categorize:
+            # the reference's Categorize option (benchmark_01.h:258-284: cell_vectorization_category =
+            # constraint mask): inside windows of the Morton order, cells with hanging nodes are moved
+            # together so that fewer warps pay for the interpolation; locality is kept at window scale
+            w = 240
+            key = (masks[order] != 0).astype(np.int64)
+            seg = (np.arange(len(order)) >= self.n_interior_cells).astype(np.int64)
+            pos = np.arange(len(order))
+            window = np.where(seg == 0, pos, pos - self.n_interior_cells) // w
+            order = order[np.lexsort((pos, key, window, seg))]
         # deal.II's cell_loop overlaps the two ghost exchanges with two interior partitions
         self.n_interior_a = self.n_interior_cells // 2 if dh.n_ranks > 1 else self.n_interior_cells
         self.cell_ids = cells[order]

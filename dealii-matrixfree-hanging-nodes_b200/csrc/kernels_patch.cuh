@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(PatchCfg<n, Number>::warps * 32, 3) patch_cell
   {
     // the 32 - cpw n idle lanes mirror lane 0 (same loads, same values stored to the
     // same addresses), so the arithmetic below needs no per-lane predicate
-    const int c = lane < cpw * n ? lane / n : 0;
-    const int t = lane < cpw * n ? lane - c * n : 0;
+    const int ml = lane < cpw * n ? lane : lane - 16; // idle lanes mirror a lane of the other half-warp
+    const int c = ml / n, t = ml - c * n;
     const bool valid     = c < info.n_cells;
     const long long cell = info.cell_begin + c;
     const unsigned mask  = (valid && p.apply_constraints) ? p.masks[cell] : 0u;

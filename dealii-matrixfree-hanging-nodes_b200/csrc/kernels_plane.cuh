@@ -261,10 +261,12 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell
   Number *A = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * 2 * Cfg::cpw * cs;
   Number *B = A + Cfg::cpw * cs;
 
-  // the 32 - cpw n idle lanes mirror lane 0 (same loads, same values stored to the same
-  // shared-memory addresses), so the arithmetic needs no per-lane predicate; they do not scatter
+  // the 32 - cpw n idle lanes mirror lane - 16 (same loads, same values stored to the same
+  // shared-memory addresses; that lane sits in the other half-warp, so no bank conflict arises),
+  // hence the arithmetic needs no per-lane predicate; they do not scatter
   const bool active = lane < Cfg::lanes;
-  const int c = active ? lane / n : 0, t = active ? lane - c * n : 0;
+  const int ml = active ? lane : lane - 16;
+  const int c = ml / n, t = ml - c * n;
   const long long cell = batch * Cfg::cpw + c;
   const bool valid = cell >= p.cell_begin && cell < p.cell_end;
   const Number *__restrict__ src = static_cast<const Number *>(p.src);

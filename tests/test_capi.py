@@ -67,10 +67,14 @@ def test_operator_creation_fails_loudly_without_gpu(mfhn):
 def test_matrix_free_host_layout(mfhn):
     tria = mfhn.Triangulation("annulus", 5, "p4est")
     dh = mfhn.DoFHandler(tria, 2)
-    mf = mfhn.MatrixFree(dh)
+    mf = mfhn.MatrixFree(dh, categorize=False)
     assert mf.n_cells == tria.n_active_cells() and mf.n_cells_hn() == tria.n_cells_with_hanging_nodes()
     assert mf.dof_indices.dtype == np.uint32 and mf.dof_indices.shape == (mf.n_cells, 27)
     assert mf.masks.dtype == np.uint8 and mf.partitioner.n_ghost == 0 and mf.partitioner.n_owned == dh.n_dofs()
     # cells are visited along the Morton curve (MatrixFree is free to reorder its batches)
     pos = tria.morton_position()
     assert (np.diff(pos[mf.cell_ids]) > 0).all()
+    # Categorize (benchmark_01.h:258-284): same cells, hanging-node cells grouped inside Morton windows
+    mfc = mfhn.MatrixFree(dh)
+    assert sorted(mfc.cell_ids) == sorted(mf.cell_ids) and mfc.n_cells_hn() == mf.n_cells_hn()
+    assert np.abs(pos[mfc.cell_ids] - np.arange(mf.n_cells)).max() < 240
