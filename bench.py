@@ -158,6 +158,19 @@ def run_cpu(args, mf, degree, n_rep, n_sample_cells=200_000, threads=None):
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: library chatter (e.g. "NCCL version ...") goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+    if line is not None:
+        print(line, flush=True)
+
+
+def run():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,7 +181,7 @@ def main():
 
     if args.impl == "reference":
         if rank != 0:
-            return
+            return None
         tria = mfhn.Triangulation(args.geometry, L, "p4est")
         dh = mfhn.DoFHandler(tria, args.degree)
         mf = mfhn.MatrixFree(dh)
@@ -185,12 +198,11 @@ def main():
         cb = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
               "sample": f"first {ns} cells of the Morton curve ({nd} DoFs per replica) of the same mesh; every thread applies the operator "
                         f"to its own vectors (benchmark_01.h:536-573); C restatement of the deal.II CPU path (deal.II itself cannot be built here)"}
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        return json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "n_dofs": dh.n_dofs()},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "wall_s": wall}))
-        return
+                          "wall_s": wall})
 
     import torch
 
@@ -248,6 +260,7 @@ def main():
         b_alg, b_alg_plain, flops = (float(x) for x in t.tolist())
     kernel_ms = float(np.mean(per)) if world == 1 else ms_per_step
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+    peak = peak * world  # aggregate over the GPUs of the job
     out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "algorithmic_bytes_without_dst_read": b_alg_plain,
                        "bytes_note": "3 s n_dofs + n_cells (4 (k+1)^3 + 1 + 3 s): src read, dst read+write (accumulating vmult), uint32 indices, mask, Cartesian geometry",
@@ -328,10 +341,9 @@ def main():
 
         out["degree_sweep"] = degree_sweep(mfhn, torch, args, time_vmult)
 
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    return json.dumps(out) if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -51,7 +51,7 @@ struct PlaneCfg
   static constexpr int ps    = round_up_mod(n * n, 1, mod);
   static constexpr int cs    = round_up_mod(n * ps, n, mod);
   static constexpr int warps = 4;
-  static constexpr int smem_per_warp = 2 * cpw * cs * (int)sizeof(Number);
+  static constexpr int smem_per_warp = cpw * cs * (int)sizeof(Number); // one array: a and b cross it one after the other
   static constexpr int smem  = warps * smem_per_warp;
 };
 
@@ -250,7 +250,7 @@ __device__ __forceinline__ void decode_mask_kernel_axes(unsigned m, unsigned &fa
 }
 
 template <int n, typename Number>
-__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell_kernel(const PlaneParams p)
+__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 3)) plane_cell_kernel(const PlaneParams p)
 {
   using Cfg = PlaneCfg<n, Number>;
   constexpr int ps = Cfg::ps, cs = Cfg::cs;
@@ -258,8 +258,7 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long batch = p.batch_begin + (long long)blockIdx.x * Cfg::warps + warp;
   if (batch >= p.batch_end) return; // warps are independent: no block-level barrier below
-  Number *A = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * 2 * Cfg::cpw * cs;
-  Number *B = A + Cfg::cpw * cs;
+  Number *A = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * Cfg::cpw * cs;
 
   // the 32 - cpw n idle lanes mirror lane - 16 (same loads, same values stored to the same
   // shared-memory addresses; that lane sits in the other half-warp, so no bank conflict arises),
@@ -272,7 +271,7 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell
   const Number *__restrict__ src = static_cast<const Number *>(p.src);
   Number *__restrict__ dst = static_cast<Number *>(p.dst);
   const uint32_t *ip = p.pidx + batch * (long long)(n * n * 32) + (c * n + t);
-  Number *cellA = A + c * cs, *cellB = B + c * cs;
+  Number *cellA = A + c * cs;
 
   // ---- P1: gather (thread = z, plane (x,y)) ---------------------------------------
   Number u[n][n];
@@ -300,43 +299,55 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, 3) plane_cell
       __syncwarp();
     }
 
-  // ---- P1: x and y sweeps ------------------------------------------------------------
+  // ---- P1: x and y sweeps (thread = Z) ----------------------------------------------
+  // a = M_Y M_X u and b = (M_Y K_X + K_Y M_X) u cross the transpose through the same
+  // shared-memory array one after the other (half the shared memory, more warps per SM)
+  Number az[n][n], bz[n][n]; // P2 operands of this thread: [Y][Z]
   {
-    Number pp[n][n], qq[n][n];
+    Number bb[n][n];
+    {
+      Number pp[n][n], qq[n][n];
 #pragma unroll
-    for (int y = 0; y < n; ++y) apply_MK<n>(u[y], pp[y], qq[y]);
+      for (int y = 0; y < n; ++y) apply_MK<n>(u[y], pp[y], qq[y]);
 #pragma unroll
-    for (int x = 0; x < n; ++x)
-      {
-        Number pc[n], qc[n], a[n], b[n];
+      for (int x = 0; x < n; ++x)
+        {
+          Number pc[n], qc[n], a[n], b[n];
 #pragma unroll
-        for (int i = 0; i < n; ++i)
-          {
-            pc[i] = pp[i][x];
-            qc[i] = qq[i][x];
-          }
-        apply_M_MK<n>(pc, qc, a, b);
+          for (int i = 0; i < n; ++i)
+            {
+              pc[i] = pp[i][x];
+              qc[i] = qq[i][x];
+            }
+          apply_M_MK<n>(pc, qc, a, b);
 #pragma unroll
-        for (int i = 0; i < n; ++i)
-          {
-            cellA[t * ps + i * n + x] = a[i];
-            cellB[t * ps + i * n + x] = b[i];
-          }
-      }
+          for (int i = 0; i < n; ++i)
+            {
+              cellA[t * ps + i * n + x] = a[i];
+              bb[i][x]                  = b[i];
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int y = 0; y < n; ++y)
+#pragma unroll
+      for (int z = 0; z < n; ++z) az[y][z] = cellA[z * ps + y * n + t];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = bb[j / n][j % n];
+    __syncwarp();
+#pragma unroll
+    for (int y = 0; y < n; ++y)
+#pragma unroll
+      for (int z = 0; z < n; ++z) bz[y][z] = cellA[z * ps + y * n + t];
   }
-  __syncwarp();
-  // ---- P2: z sweep (thread = x) ------------------------------------------------------
+  // ---- P2: Z sweep (thread = X) ------------------------------------------------------
 #pragma unroll
   for (int y = 0; y < n; ++y)
     {
-      Number a[n], b[n], r[n];
-#pragma unroll
-      for (int z = 0; z < n; ++z)
-        {
-          a[z] = cellA[z * ps + y * n + t];
-          b[z] = cellB[z * ps + y * n + t];
-        }
-      apply_Mb_Ka<n>(a, b, r);
+      Number r[n];
+      apply_Mb_Ka<n>(az[y], bz[y], r);
 #pragma unroll
       for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
     }
