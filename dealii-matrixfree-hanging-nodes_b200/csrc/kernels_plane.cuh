@@ -67,7 +67,22 @@ struct PlaneParams
   void *dst;
   long long cell_begin, cell_end, batch_begin, batch_end;
   int apply_constraints;
+  cudaTextureObject_t src_tex; // src bound as a linear texture: gathers go through the TEX pipe
 };
+
+template <typename Number>
+__device__ __forceinline__ Number tex_fetch(cudaTextureObject_t tex, uint32_t i);
+template <>
+__device__ __forceinline__ double tex_fetch<double>(cudaTextureObject_t tex, uint32_t i)
+{
+  const int2 v = tex1Dfetch<int2>(tex, (int)i);
+  return __hiloint2double(v.y, v.x);
+}
+template <>
+__device__ __forceinline__ float tex_fetch<float>(cudaTextureObject_t tex, uint32_t i)
+{
+  return tex1Dfetch<float>(tex, (int)i);
+}
 
 // ---- even-odd application of a persymmetric matrix --------------------------
 template <int n, typename Number>
@@ -249,7 +264,7 @@ __device__ __forceinline__ void decode_mask_kernel_axes(unsigned m, unsigned &fa
   cb   = rot3(cb);
 }
 
-template <int n, typename Number>
+template <int n, typename Number, bool TEX>
 __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 3)) plane_cell_kernel(const PlaneParams p)
 {
   using Cfg = PlaneCfg<n, Number>;
@@ -280,7 +295,8 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
 #pragma unroll
     for (int j = 0; j < n * n; ++j) idx[j] = valid ? __ldg(ip + j * 32) : 0xffffffffu;
 #pragma unroll
-    for (int j = 0; j < n * n; ++j) u[j / n][j % n] = (idx[j] != 0xffffffffu) ? __ldg(src + idx[j]) : Number(0);
+    for (int j = 0; j < n * n; ++j)
+      u[j / n][j % n] = (idx[j] != 0xffffffffu) ? (TEX ? tex_fetch<Number>(p.src_tex, idx[j]) : __ldg(src + idx[j])) : Number(0);
   }
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
@@ -384,13 +400,15 @@ struct PlaneLayout
 };
 
 template <int n, typename Number>
-void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream)
+void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex)
 {
   using Cfg = PlaneCfg<n, Number>;
   static bool attr[64] = {};
   if (!attr[device])
     {
-      cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
+      cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
       if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       attr[device] = true;
     }
@@ -406,19 +424,23 @@ void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.batch_begin       = cp.cell_begin / Cfg::cpw;
   p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
+  p.src_tex           = tex;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + Cfg::warps - 1) / Cfg::warps);
-  plane_cell_kernel<n, Number><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+  if (tex)
+    plane_cell_kernel<n, Number, true><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+  else
+    plane_cell_kernel<n, Number, false><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("plane kernel launch: ") + cudaGetErrorString(e));
 }
 
 template <int n, typename Number>
-void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream)
+void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex)
 {
   if constexpr (plane_supported(n))
-    launch_plane_impl<n, Number>(L, cp, device, stream);
+    launch_plane_impl<n, Number>(L, cp, device, stream, tex);
   else
     throw std::runtime_error("plane kernel not available for this degree");
 }

@@ -7,12 +7,14 @@
 #include "kernels_generic.cuh"
 #include "kernels_plane.cuh"
 #include "kernels_patch.cuh"
+#include "kernels_plane_smem.cuh"
 #include "octree.hpp"
 
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 #include <algorithm>
 #include <mutex>
@@ -250,6 +252,37 @@ struct Operator
   std::vector<long long> segments;
   long long launches = 0;
   void *d_stage_src = nullptr, *d_stage_dst = nullptr; // device staging of the host-buffer entry point
+  // src vectors bound as linear textures (gathers through the TEX pipe), cached per pointer
+  int use_texture = 0; // measured: no gain over plain loads (profiles/), kept as a switch (MFHN_TEXTURE=1)
+  std::vector<std::pair<const void *, cudaTextureObject_t>> tex_cache;
+  cudaTextureObject_t texture_for(const void *src)
+  {
+    if (!use_texture) return 0;
+    for (auto &e : tex_cache)
+      if (e.first == src) return e.second;
+    const long long nvec = n_owned + n_ghost;
+    cudaResourceDesc rd{};
+    rd.resType                = cudaResourceTypeLinear;
+    rd.res.linear.devPtr      = const_cast<void *>(src);
+    rd.res.linear.desc        = number == MFHN_F64 ? cudaCreateChannelDesc<int2>() : cudaCreateChannelDesc<float>();
+    rd.res.linear.sizeInBytes = (size_t)nvec * (number == MFHN_F64 ? 8 : 4);
+    cudaTextureDesc td{};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t t = 0;
+    if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess)
+      {
+        cudaGetLastError(); // vector too long for a linear texture: fall back to plain loads
+        use_texture = 0;
+        return 0;
+      }
+    if (tex_cache.size() >= 16)
+      {
+        cudaDestroyTextureObject(tex_cache.front().second);
+        tex_cache.erase(tex_cache.begin());
+      }
+    tex_cache.emplace_back(src, t);
+    return t;
+  }
 
   ~Operator()
   {
@@ -258,6 +291,7 @@ struct Operator
     cudaFree(d_geom);
     cudaFree(d_stage_src);
     cudaFree(d_stage_dst);
+    for (auto &e : tex_cache) cudaDestroyTextureObject(e.second);
     plane.free();
     patch.free();
   }
@@ -287,8 +321,10 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
 {
   if (kernel == MFHN_KERNEL_PATCH)
     launch_patch<n, Number>(op.patch, p, op.device, stream);
-  else if (kernel == MFHN_KERNEL_PLANE)
-    launch_plane<n, Number>(op.plane, p, op.device, stream);
+  else if (kernel == MFHN_KERNEL_PLANE && plane_supported(n))
+    launch_plane<n, Number>(op.plane, p, op.device, stream, op.texture_for(p.src));
+  else if (kernel == MFHN_KERNEL_PLANE) // degrees 6..8: plane in shared memory
+    launch_plane_smem<n, Number>(op.plane, p, op.device, stream);
   else if (op.geometry_type == MFHN_GEOM_AFFINE)
     launch_generic<n, Number, GV_QPOINT_METRIC>(op, p, stream);
   else if (kernel == MFHN_KERNEL_SEPARABLE)
@@ -319,12 +355,11 @@ int resolve_kernel(const Operator &op)
 {
   int kernel = op.kernel;
   if (kernel == MFHN_KERNEL_AUTO)
-    kernel = (op.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(op.degree + 1)) ? MFHN_KERNEL_PLANE :
-             (op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_SEPARABLE : MFHN_KERNEL_QPOINT);
+    kernel = op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_PLANE : MFHN_KERNEL_QPOINT;
   if (op.geometry_type == MFHN_GEOM_AFFINE && kernel != MFHN_KERNEL_QPOINT)
     throw InvalidArgument("affine geometry requires MFHN_KERNEL_QPOINT");
-  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH) && !plane_supported(op.degree + 1))
-    throw NotImplemented("MFHN_KERNEL_PLANE / MFHN_KERNEL_PATCH are not available for this degree");
+  if (kernel == MFHN_KERNEL_PATCH && !plane_supported(op.degree + 1))
+    throw NotImplemented("MFHN_KERNEL_PATCH is not available for this degree");
   if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
   if (kernel == MFHN_KERNEL_BASELINE) throw NotImplemented("MFHN_KERNEL_BASELINE is not built yet");
@@ -371,6 +406,7 @@ Operator *op_create(const mfhn_op_desc &d)
   op->device            = device;
   op->geometry_type     = d.geometry_type;
   op->apply_constraints = d.apply_constraints;
+  if (const char *e = std::getenv("MFHN_TEXTURE")) op->use_texture = std::atoi(e);
   op->kernel            = d.kernel;
   op->n_cells           = d.n_cells;
   op->n_owned           = d.n_owned;
@@ -419,7 +455,7 @@ Operator *op_create(const mfhn_op_desc &d)
       std::vector<float> gf(g.begin(), g.end());
       op->d_geom = to_device(gf);
     }
-  if (d.geometry_type == MFHN_GEOM_CARTESIAN && plane_supported(n))
+  if (d.geometry_type == MFHN_GEOM_CARTESIAN)
     {
       const Shape1D sh = make_shape(d.degree);
       op->plane.build(n, d.number, d.n_cells, d.dof_indices, sh.W[0].data());
@@ -431,7 +467,7 @@ Operator *op_create(const mfhn_op_desc &d)
           for (int i = 1; i < d.n_segments; ++i)
             if (d.segments[i] < d.segments[i - 1] || d.segments[i] > d.n_cells) throw InvalidArgument("segments must be ascending");
         }
-      op->patch.build(n, d.number, d.n_cells, d.dof_indices, op->segments);
+      if (plane_supported(n)) op->patch.build(n, d.number, d.n_cells, d.dof_indices, op->segments);
     }
   resolve_kernel(*op);
   return op.release();
