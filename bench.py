@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="timed loop only (for profiler runs)")
+    ap.add_argument("--no-graph", action="store_true", help="partitioned runs: launch every vmult from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -116,8 +117,14 @@ def default_refinements(args):
     return 8 if args.degree <= 4 else 7
 
 
-def time_vmult(torch, op, dst, src, steps, warmup, barrier=None):
+def time_vmult(torch, op, dst, src, steps, warmup, barrier=None, graph=None):
     """K steps bracketed by synchronize (+barrier), per-launch CUDA events on the launching stream."""
+    if graph is not None:
+        class _G:
+            @staticmethod
+            def vmult(d, s):
+                graph.replay()
+        op = _G
     for _ in range(warmup):
         op.vmult(dst, src)
     torch.cuda.synchronize()
@@ -224,8 +231,12 @@ def run():
     prob["fill_src"](src)
     t_setup = time.perf_counter() - t_setup
 
+    graph = None
+    if world > 1 and not args.no_graph:
+        graph = prob["comm"].capture(op, dst, src)
+        dst.zero_()
     with ClockSampler(local_rank) as clocks:
-        total_ms, per = time_vmult(torch, op, dst, src, args.steps, args.warmup, barrier)
+        total_ms, per = time_vmult(torch, op, dst, src, args.steps, args.warmup, barrier, graph)
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,7 +281,8 @@ def run():
     out["config"] = {"workload": workload, "n_cells": int(prob["n_cells_global"]), "n_cells_hn": int(prob["n_cells_hn_global"]),
                      "n_dofs": int(n_dofs_global), "kernel": prob["kernel_name"], "partition": prob["partition"],
                      "l2": "inputs larger than L2 (vectors + index arrays >> 126 MB), no flush",
-                     "dst": "accumulating vmult like benchmark_03.h:352", "setup_s": round(t_setup, 1)}
+                     "dst": "accumulating vmult like benchmark_03.h:352", "setup_s": round(t_setup, 1),
+                     "launch": "CUDA graph replay of one partitioned vmult" if graph is not None else "host launches"}
 
     if rank == 0 and world == 1 and not args.minimal:
         # hanging-node overhead on the same mesh and index arrays (benchmark_03.h:255-268)
