@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="timed loop only (for profiler runs)")
-    ap.add_argument("--no-graph", action="store_true", help="partitioned runs: launch every vmult from the host instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="partitioned runs: replay a CUDA graph of one vmult (experimental: the capture of the NCCL p2p groups hung on this pool, so it is off by default)")
     return ap.parse_args()
 
 
@@ -232,7 +232,7 @@ def run():
     t_setup = time.perf_counter() - t_setup
 
     graph = None
-    if world > 1 and not args.no_graph:
+    if world > 1 and args.graph:
         graph = prob["comm"].capture(op, dst, src)
         dst.zero_()
     with ClockSampler(local_rank) as clocks:
