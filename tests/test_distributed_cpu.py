@@ -78,7 +78,7 @@ def test_partitioned_vmult_matches_serial(world, geo, L, k, w):
     assert n_cells == tria.n_active_cells()
     # every ghost entry of one rank is an import entry of its owner (benchmark_02.cc:164-165 logs both)
     assert sum(res[r][3] for r in range(world)) == sum(res[r][4] for r in range(world)) > 0
-    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-13
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-12
     # the numbering itself: same DoF count as the serial enumeration, ranges tile [0, n_dofs)
     assert dh.n_dofs() == mfhn.DoFHandler(tria, k).n_dofs()
     assert [res[r][0] for r in range(world)] == [0] + [res[r][1] for r in range(world - 1)]
