@@ -111,7 +111,15 @@ class ClockSampler:
 def default_refinements(args):
     if args.refinements is not None:
         return args.refinements
+    if args.geometry == "annulus" and args.degree == 4 and int(os.environ.get("WORLD_SIZE", "1")) == 8:
+        return 10  # weak scaling: 1.124 B DoFs on 8 GPUs = 140.5 M per GPU (N=1: 142.8 M)
     # SURVEY 8d / BASELINE.md C2: annulus (p4est flavour) L=9 for k <= 4 (142.8 M DoFs at k=4), L=8 for k >= 5
+    if args.geometry == "annulus":
+        return 9 if args.degree <= 4 else 8
+    return 8 if args.degree <= 4 else 7
+
+
+def default_refinements_single(args):
     if args.geometry == "annulus":
         return 9 if args.degree <= 4 else 8
     return 8 if args.degree <= 4 else 7
@@ -255,7 +263,7 @@ def run():
         del ones, chk
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.refinements is not None and world > 1 else ("strong" if world > 1 else "weak"), "vs_baseline": None,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 or L != default_refinements_single(args) else "strong", "vs_baseline": None,
            "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic"}
     launches_per_step = prob["launches_per_step"]
     out["gpu_launches"] = int(launches_per_step * args.steps)
@@ -273,7 +281,12 @@ def run():
     kernel_ms = float(np.mean(per)) if world == 1 else ms_per_step
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     peak = peak * world  # aggregate over the GPUs of the job
-    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{args.geometry}_L{L}_k{args.degree}_{args.number}_{prob['kernel_name']}")
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "algorithmic_bytes_without_dst_read": b_alg_plain,
                        "bytes_note": "3 s n_dofs + n_cells (4 (k+1)^3 + 1 + 3 s): src read, dst read+write (accumulating vmult), uint32 indices, mask, Cartesian geometry",
                        "kernel_ms_min_avg_max": [float(per.min()), float(per.mean()), float(per.max())],
@@ -312,23 +325,39 @@ def run():
         hd = torch.empty(n_local, dtype=src.dtype).pin_memory()
         hs.copy_(src.cpu())
         e_steps = max(3, min(args.steps, 10))
-        def host_step():
-            if world == 1:
-                op.vmult_host(hd, hs, zero_dst=True)  # C ABI entry point on host vectors
-            else:
-                src.copy_(hs, non_blocking=True)
-                op.vmult(dst, src, zero_dst=True)  # ghost import / compress inside
-                hd.copy_(dst, non_blocking=True)
+        # two host buffer pairs / device staging slots / streams: the upload of step i+1 overlaps the
+        # download of step i (full-duplex PCIe); every step still moves its own src up and dst down
+        hs2 = torch.empty(n_local, dtype=src.dtype).pin_memory()
+        hd2 = torch.empty(n_local, dtype=src.dtype).pin_memory()
+        hs2.copy_(hs)
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        bufs = [(hd, hs), (hd2, hs2)]
 
-        for _ in range(2):
-            host_step()
+        def host_step(i):
+            with torch.cuda.stream(streams[i % 2]):
+                d_, s_ = bufs[i % 2]
+                if world == 1:
+                    op.vmult_host(d_, s_, zero_dst=True, slot=i % 2)  # C ABI entry point on host vectors
+                else:
+                    src.copy_(s_, non_blocking=True)
+                    op.vmult(dst, src, zero_dst=True)  # ghost import / compress inside
+                    d_.copy_(dst, non_blocking=True)
+
+        if world > 1:
+            streams = [torch.cuda.current_stream(), torch.cuda.current_stream()]  # one vector pair: no overlap across steps
+        for i in range(2):
+            host_step(i)
         torch.cuda.synchronize()
         if barrier:
             barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(e_steps):
-            host_step()
+        for s_ in streams:
+            s_.wait_stream(torch.cuda.current_stream())
+        for i in range(e_steps):
+            host_step(i)
+        for s_ in streams:
+            torch.cuda.current_stream().wait_stream(s_)
         e1.record()
         torch.cuda.synchronize()
         if barrier:
@@ -341,7 +370,8 @@ def run():
         esz = src.element_size()
         out["e2e"] = {"value": n_dofs_global / (e_ms / e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_local * esz),
                       "d2h_bytes_per_step": int(n_local * esz), "steps": e_steps,
-                      "note": "mfhn_op_vmult_host: pinned host src -> device, vmult into a zeroed device dst, dst -> pinned host; PCIe-bound"}
+                      "note": "mfhn_op_vmult_host_slot: pinned host src -> device, vmult into a zeroed device dst, dst -> pinned host, every step; "
+                              "two staging slots on two streams so that the upload of step i+1 overlaps the download of step i; PCIe-bound"}
         if world > 1:
             out["e2e"]["note"] = "per rank: pinned host src -> device, partitioned vmult with ghost exchange, dst -> pinned host; bytes are per rank"
 

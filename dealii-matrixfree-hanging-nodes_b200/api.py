@@ -289,15 +289,16 @@ class LaplaceOperator:
         else:
             self._comm.vmult(self, dst, src, zero_dst)
 
-    def vmult_host(self, dst_host, src_host, zero_dst=True):
+    def vmult_host(self, dst_host, src_host, zero_dst=True, slot=0):
         """vmult on HOST vectors (torch CPU tensors, ideally pinned): H2D, kernel, D2H,
-        all stream-ordered on the current stream."""
+        all stream-ordered on the current stream.  Calls with different `slot` (0/1) on
+        different streams may overlap (upload of one application, download of the other)."""
         torch = _torch()
         for v in (dst_host, src_host):
             if v.is_cuda or v.dtype != self.dtype or not v.is_contiguous() or v.numel() != self.n_owned + self.n_ghost:
                 raise capi.MfhnError(1, "host vector has the wrong type or size")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        check(lib.mfhn_op_vmult_host(self._h, dst_host.data_ptr(), src_host.data_ptr(), stream, int(zero_dst)))
+        check(lib.mfhn_op_vmult_host_slot(self._h, dst_host.data_ptr(), src_host.data_ptr(), stream, int(zero_dst), slot))
 
     # -- switches / queries ----------------------------------------------------
     def set_apply_constraints(self, flag: bool):

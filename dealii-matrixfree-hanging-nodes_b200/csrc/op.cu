@@ -251,7 +251,7 @@ struct Operator
   PatchLayout patch;            // sorted-unique / CSR layout of the patch kernel
   std::vector<long long> segments;
   long long launches = 0;
-  void *d_stage_src = nullptr, *d_stage_dst = nullptr; // device staging of the host-buffer entry point
+  void *d_stage_src[2] = {nullptr, nullptr}, *d_stage_dst[2] = {nullptr, nullptr}; // device staging of the host-vector entry point (2 slots)
   // src vectors bound as linear textures (gathers through the TEX pipe), cached per pointer
   int use_texture = 0; // measured: no gain over plain loads (profiles/), kept as a switch (MFHN_TEXTURE=1)
   std::vector<std::pair<const void *, cudaTextureObject_t>> tex_cache;
@@ -289,8 +289,11 @@ struct Operator
     cudaFree(d_idx);
     cudaFree(d_masks);
     cudaFree(d_geom);
-    cudaFree(d_stage_src);
-    cudaFree(d_stage_dst);
+    for (int i = 0; i < 2; ++i)
+      {
+        cudaFree(d_stage_src[i]);
+        cudaFree(d_stage_dst[i]);
+      }
     for (auto &e : tex_cache) cudaDestroyTextureObject(e.second);
     plane.free();
     patch.free();
@@ -586,27 +589,32 @@ int mfhn_op_vmult_range(mfhn_op h, void *dst, const void *src, void *stream, int
     op_vmult_range(op, dst, src, static_cast<cudaStream_t>(stream), cb, ce);
   });
 }
-int mfhn_op_vmult_host(mfhn_op h, void *dst_host, const void *src_host, void *stream, int zero_dst)
+int mfhn_op_vmult_host_slot(mfhn_op h, void *dst_host, const void *src_host, void *stream, int zero_dst, int slot)
 {
   return guard([&] {
     if (!h || !dst_host || !src_host) throw InvalidArgument("null argument");
+    if (slot < 0 || slot > 1) throw InvalidArgument("slot must be 0 or 1");
     Operator &op = *reinterpret_cast<Operator *>(h);
     CUDA_CHECK(cudaSetDevice(op.device));
     cudaStream_t st    = static_cast<cudaStream_t>(stream);
     const size_t bytes = (size_t)(op.n_owned + op.n_ghost) * (op.number == MFHN_F64 ? 8 : 4);
-    if (!op.d_stage_src)
+    if (!op.d_stage_src[slot])
       {
-        CUDA_CHECK(cudaMalloc(&op.d_stage_src, std::max<size_t>(bytes, 8)));
-        CUDA_CHECK(cudaMalloc(&op.d_stage_dst, std::max<size_t>(bytes, 8)));
+        CUDA_CHECK(cudaMalloc(&op.d_stage_src[slot], std::max<size_t>(bytes, 8)));
+        CUDA_CHECK(cudaMalloc(&op.d_stage_dst[slot], std::max<size_t>(bytes, 8)));
       }
-    CUDA_CHECK(cudaMemcpyAsync(op.d_stage_src, src_host, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(op.d_stage_src[slot], src_host, bytes, cudaMemcpyHostToDevice, st));
     if (zero_dst)
-      CUDA_CHECK(cudaMemsetAsync(op.d_stage_dst, 0, bytes, st));
+      CUDA_CHECK(cudaMemsetAsync(op.d_stage_dst[slot], 0, bytes, st));
     else
-      CUDA_CHECK(cudaMemcpyAsync(op.d_stage_dst, dst_host, bytes, cudaMemcpyHostToDevice, st));
-    op_vmult_range(op, op.d_stage_dst, op.d_stage_src, st, 0, op.n_cells);
-    CUDA_CHECK(cudaMemcpyAsync(dst_host, op.d_stage_dst, bytes, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(op.d_stage_dst[slot], dst_host, bytes, cudaMemcpyHostToDevice, st));
+    op_vmult_range(op, op.d_stage_dst[slot], op.d_stage_src[slot], st, 0, op.n_cells);
+    CUDA_CHECK(cudaMemcpyAsync(dst_host, op.d_stage_dst[slot], bytes, cudaMemcpyDeviceToHost, st));
   });
+}
+int mfhn_op_vmult_host(mfhn_op h, void *dst_host, const void *src_host, void *stream, int zero_dst)
+{
+  return mfhn_op_vmult_host_slot(h, dst_host, src_host, stream, zero_dst, 0);
 }
 int mfhn_op_set_apply_constraints(mfhn_op h, int v)
 {

@@ -156,6 +156,11 @@ int mfhn_op_vmult_range(mfhn_op op, void *dst, const void *src, void *cuda_strea
  * LaplaceOperator<...,MemorySpace::Host>::vmult (benchmark_03.h:237-241) binds. */
 int mfhn_op_vmult_host(mfhn_op op, void *dst_host, const void *src_host, void *cuda_stream,
                        int zero_dst);
+/* Same with an explicit device staging slot (0 or 1): two calls on different
+ * streams and different slots may be in flight at once, so the upload of one
+ * application overlaps the download of the previous one (full-duplex PCIe). */
+int mfhn_op_vmult_host_slot(mfhn_op op, void *dst_host, const void *src_host, void *cuda_stream,
+                            int zero_dst, int slot);
 
 /* Change the apply_constraints switch / kernel of an existing operator. */
 int mfhn_op_set_apply_constraints(mfhn_op op, int apply_constraints);

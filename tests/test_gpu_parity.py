@@ -221,3 +221,25 @@ def test_cpp_driver_over_c_abi(mfhn):
     assert abs(got - ref) / ref < 1e-10
     cols = out.splitlines()[1].split()
     assert int(cols[3]) == lay.n_cells and int(cols[5]) == lay.n_dofs and int(cols[4]) == int((lay.masks != 0).sum())
+
+
+def test_host_vector_entry_point(mfhn):
+    """mfhn_op_vmult_host[_slot]: the call a host-vector caller binds (LaplaceOperator<...,Host>::vmult,
+    benchmark_03.h:237-241): same result as the device-vector path, both staging slots, accumulate and zero."""
+    import torch
+
+    dh, mf, lay = _case(mfhn, "annulus", 5, "p4est", 2)
+    x = _src(lay, "random")
+    ref = operators.vmult_fast(lay, x)
+    op = mfhn.LaplaceOperator(mf)
+    hs = torch.from_numpy(x.copy()).pin_memory()
+    for slot in (0, 1):
+        hd = torch.zeros(lay.n_dofs, dtype=torch.float64).pin_memory()
+        op.vmult_host(hd, hs, zero_dst=True, slot=slot)
+        torch.cuda.synchronize()
+        assert np.abs(hd.numpy() - ref).max() / np.abs(ref).max() < 1e-12
+        op.vmult_host(hd, hs, zero_dst=False, slot=slot)  # accumulates like the reference
+        torch.cuda.synchronize()
+        assert np.abs(hd.numpy() - 2 * ref).max() / np.abs(ref).max() < 1e-12
+    with pytest.raises(mfhn.MfhnError):
+        op.vmult_host(hd, hs, slot=2)
