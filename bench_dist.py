@@ -27,7 +27,8 @@ def build_problem(mfhn, args, L, rank, world):
         op = mfhn.LaplaceOperator(mf, number=args.number, kernel=args.kernel)
         comm = distributed.GhostExchange(op)
         op.attach_communicator(comm)
-        partition = f"Morton (p4est-like) partition into {world} ranks, NCCL ghost import/compress overlapped with interior cells"
+        how = "one C-ABI call per vmult (NCCL groups issued from C++)" if comm._native is not None else "torch.distributed p2p groups"
+        partition = f"Morton (p4est-like) partition into {world} ranks, NCCL ghost import/compress overlapped with interior cells, {how}"
         launches = comm.launches_per_vmult()
 
     def fill_src(src):

@@ -42,6 +42,23 @@ class OpDesc(C.Structure):
     ]
 
 
+class DistDesc(C.Structure):
+    _fields_ = [
+        ("rank", c_int),
+        ("world", c_int),
+        ("unique_id", c_void_p),
+        ("n_import_peers", c_int),
+        ("import_peers", c_void_p),
+        ("import_offsets", c_void_p),
+        ("import_indices", c_void_p),
+        ("n_ghost_peers", c_int),
+        ("ghost_peers", c_void_p),
+        ("ghost_begin", c_void_p),
+        ("ghost_end", c_void_p),
+        ("segments", c_int64 * 4),
+    ]
+
+
 # every symbol include/mfhn.h declares: (restype, argtypes)
 SIGNATURES = {
     "mfhn_last_error": (c_char_p, []),
@@ -79,6 +96,11 @@ SIGNATURES = {
     "mfhn_pack": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mfhn_unpack_add": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mfhn_bench_dfma": (c_int, [c_int, c_int, P(c_double)]),
+    "mfhn_dist_unique_id": (c_int, [c_void_p]),
+    "mfhn_dist_create": (c_int, [c_void_p, P(DistDesc), P(c_void_p)]),
+    "mfhn_dist_destroy": (None, [c_void_p]),
+    "mfhn_dist_vmult": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "mfhn_dist_launch_count": (c_int64, [c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

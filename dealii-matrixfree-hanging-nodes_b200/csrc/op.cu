@@ -8,6 +8,7 @@
 #include "kernels_plane.cuh"
 #include "kernels_patch.cuh"
 #include "kernels_plane_smem.cuh"
+#include "dist.cuh"
 #include "octree.hpp"
 
 #include <cuda_runtime.h>
@@ -554,6 +555,103 @@ __global__ void fma_bench_kernel(Number *out, int iters)
   for (int i = 0; i < 8; ++i) s += a[i];
   if (s == Number(-1)) out[0] = s;
 }
+
+// ---------------------------------------------------------------------------
+// partitioned operator: ghost import / compress over NCCL, overlapped with the cell partitions
+struct Dist
+{
+  Operator *op = nullptr;
+  void *comm   = nullptr;
+  int rank = 0, world = 1;
+  std::vector<int> import_peers, ghost_peers;
+  std::vector<long long> import_off, ghost_begin, ghost_end;
+  long long n_import = 0;
+  long long seg[4]   = {0, 0, 0, 0};
+  int32_t *d_import_idx = nullptr;
+  void *d_send = nullptr, *d_recv = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev[4]        = {nullptr, nullptr, nullptr, nullptr};
+  long long launches       = 0;
+
+  ~Dist()
+  {
+    if (comm) NcclApi::get().CommDestroy(comm);
+    cudaFree(d_import_idx);
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
+    for (auto e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
+#define NCCL_CHECK(x)                                                                            \
+  do                                                                                             \
+    {                                                                                            \
+      int r_ = (x);                                                                              \
+      if (r_ != 0) throw CudaError(std::string(#x) + ": " + NcclApi::get().GetErrorString(r_)); \
+    }                                                                                            \
+  while (0)
+
+void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero_dst)
+{
+  Operator &op  = *d.op;
+  NcclApi &nccl = NcclApi::get();
+  const size_t s = op.number == MFHN_F64 ? 8 : 4;
+  char *dstb = static_cast<char *>(dst);
+  char *srcb = static_cast<char *>(const_cast<void *>(src));
+  const unsigned grid = (unsigned)((d.n_import + 255) / 256);
+  if (zero_dst) CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)(op.n_owned + op.n_ghost) * s, main));
+  // pack the entries the peers ghost
+  if (d.n_import > 0)
+    {
+      if (op.number == MFHN_F64)
+        pack_all_kernel<double><<<grid, 256, 0, main>>>((double *)d.d_send, (const double *)src, d.d_import_idx, d.n_import);
+      else
+        pack_all_kernel<float><<<grid, 256, 0, main>>>((float *)d.d_send, (const float *)src, d.d_import_idx, d.n_import);
+      CUDA_CHECK(cudaGetLastError());
+      ++d.launches;
+    }
+  CUDA_CHECK(cudaEventRecord(d.ev[0], main));
+  CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[0], 0));
+  // owners -> ghosts (update_ghost_values)
+  NCCL_CHECK(nccl.GroupStart());
+  for (size_t i = 0; i < d.ghost_peers.size(); ++i)
+    NCCL_CHECK(nccl.Recv(srcb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
+                         d.ghost_peers[i], d.comm, d.comm_stream));
+  for (size_t i = 0; i < d.import_peers.size(); ++i)
+    NCCL_CHECK(nccl.Send(static_cast<char *>(d.d_send) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
+                         d.import_peers[i], d.comm, d.comm_stream));
+  NCCL_CHECK(nccl.GroupEnd());
+  CUDA_CHECK(cudaEventRecord(d.ev[1], d.comm_stream));
+  if (d.seg[1] > d.seg[0]) op_vmult_range(op, dst, src, main, d.seg[0], d.seg[1]); // interior A overlaps the import
+  CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[1], 0));
+  if (d.seg[3] > d.seg[2]) op_vmult_range(op, dst, src, main, d.seg[2], d.seg[3]); // boundary cells need the ghosts
+  CUDA_CHECK(cudaEventRecord(d.ev[2], main));
+  CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[2], 0));
+  // ghosts -> owners (compress, add)
+  NCCL_CHECK(nccl.GroupStart());
+  for (size_t i = 0; i < d.import_peers.size(); ++i)
+    NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
+                         d.import_peers[i], d.comm, d.comm_stream));
+  for (size_t i = 0; i < d.ghost_peers.size(); ++i)
+    NCCL_CHECK(nccl.Send(dstb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
+                         d.ghost_peers[i], d.comm, d.comm_stream));
+  NCCL_CHECK(nccl.GroupEnd());
+  CUDA_CHECK(cudaEventRecord(d.ev[3], d.comm_stream));
+  if (d.seg[2] > d.seg[1]) op_vmult_range(op, dst, src, main, d.seg[1], d.seg[2]); // interior B overlaps the compress
+  CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
+  if (d.n_import > 0)
+    {
+      if (op.number == MFHN_F64)
+        unpack_add_all_kernel<double><<<grid, 256, 0, main>>>((double *)dst, (const double *)d.d_recv, d.d_import_idx, d.n_import);
+      else
+        unpack_add_all_kernel<float><<<grid, 256, 0, main>>>((float *)dst, (const float *)d.d_recv, d.d_import_idx, d.n_import);
+      CUDA_CHECK(cudaGetLastError());
+      ++d.launches;
+    }
+  if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(dstb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
+}
 } // namespace mfhn
 
 using namespace mfhn;
@@ -744,4 +842,63 @@ int mfhn_bench_dfma(int number, int iters, double *tflops)
     cudaFree(out);
   });
 }
+
+int mfhn_dist_unique_id(void *id128)
+{
+  return guard([&] {
+    if (!id128) throw InvalidArgument("null argument");
+    NcclApi &nccl = NcclApi::get();
+    if (!nccl.ok) throw CudaError(nccl.error);
+    NCCL_CHECK(nccl.GetUniqueId(id128));
+  });
+}
+int mfhn_dist_create(mfhn_op h, const mfhn_dist_desc *dd, mfhn_dist *out)
+{
+  return guard([&] {
+    if (!h || !dd || !out || !dd->unique_id) throw InvalidArgument("null argument");
+    NcclApi &nccl = NcclApi::get();
+    if (!nccl.ok) throw CudaError(nccl.error);
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    std::unique_ptr<Dist> d(new Dist);
+    d->op    = &op;
+    d->rank  = dd->rank;
+    d->world = dd->world;
+    for (int i = 0; i < 4; ++i) d->seg[i] = dd->segments[i];
+    if (!(0 == d->seg[0] && d->seg[0] <= d->seg[1] && d->seg[1] <= d->seg[2] && d->seg[2] <= d->seg[3] && d->seg[3] == op.n_cells))
+      throw InvalidArgument("segments must be 0 <= a <= b <= n_cells");
+    d->import_peers.assign(dd->import_peers, dd->import_peers + dd->n_import_peers);
+    d->import_off.assign(dd->import_offsets, dd->import_offsets + dd->n_import_peers + 1);
+    d->ghost_peers.assign(dd->ghost_peers, dd->ghost_peers + dd->n_ghost_peers);
+    d->ghost_begin.assign(dd->ghost_begin, dd->ghost_begin + dd->n_ghost_peers);
+    d->ghost_end.assign(dd->ghost_end, dd->ghost_end + dd->n_ghost_peers);
+    d->n_import = d->import_off.back();
+    for (long long i = 0; i < d->n_import; ++i)
+      if (dd->import_indices[i] < 0 || dd->import_indices[i] >= op.n_owned) throw InvalidArgument("import index out of range");
+    for (size_t i = 0; i < d->ghost_peers.size(); ++i)
+      if (d->ghost_begin[i] < 0 || d->ghost_end[i] > op.n_ghost || d->ghost_begin[i] > d->ghost_end[i]) throw InvalidArgument("ghost range out of bounds");
+    const size_t s = op.number == MFHN_F64 ? 8 : 4;
+    CUDA_CHECK(cudaMalloc(&d->d_import_idx, std::max<size_t>(1, d->n_import) * sizeof(int32_t)));
+    CUDA_CHECK(cudaMemcpy(d->d_import_idx, dd->import_indices, d->n_import * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMalloc(&d->d_send, std::max<size_t>(8, d->n_import * s)));
+    CUDA_CHECK(cudaMalloc(&d->d_recv, std::max<size_t>(8, d->n_import * s)));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+    for (auto &e : d->ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    NcclApi::Id id;
+    std::memcpy(&id, dd->unique_id, sizeof(id));
+    NCCL_CHECK(nccl.CommInitRank(&d->comm, dd->world, id, dd->rank));
+    *out = reinterpret_cast<mfhn_dist>(d.release());
+  });
+}
+void mfhn_dist_destroy(mfhn_dist d) { delete reinterpret_cast<Dist *>(d); }
+int mfhn_dist_vmult(mfhn_dist h, void *dst, const void *src, void *stream, int zero_dst)
+{
+  return guard([&] {
+    if (!h || !dst || !src) throw InvalidArgument("null argument");
+    Dist &d = *reinterpret_cast<Dist *>(h);
+    CUDA_CHECK(cudaSetDevice(d.op->device));
+    dist_vmult(d, dst, src, static_cast<cudaStream_t>(stream), zero_dst);
+  });
+}
+int64_t mfhn_dist_launch_count(mfhn_dist h) { return h ? reinterpret_cast<Dist *>(h)->launches : 0; }
 }

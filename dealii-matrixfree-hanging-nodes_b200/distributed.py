@@ -29,7 +29,8 @@ class GhostExchange:
     loop on a cell range; by default the CUDA operator's vmult_range.  The CPU
     tests pass the oracle here to exercise the exchange logic under gloo."""
 
-    def __init__(self, op=None, partitioner=None, segments=None, local_apply=None, device=None, dtype=None, group=None):
+    def __init__(self, op=None, partitioner=None, segments=None, local_apply=None, device=None, dtype=None, group=None,
+                 native=None):
         import torch
         import torch.distributed as dist
 
@@ -57,6 +58,45 @@ class GhostExchange:
         if self.cuda:
             self.comm_stream = torch.cuda.Stream(device=self.device)
         self.n_launches = 0
+        # native path: the whole schedule (pack, NCCL groups, cell partitions, unpack) in one C-ABI call
+        self._native = None
+        if native is None:
+            native = self.cuda and op is not None and local_apply is None and dist.get_backend(group) == "nccl"
+        if native:
+            self._create_native(op)
+
+    def _create_native(self, op):
+        import ctypes as C
+
+        torch, dist, part = self.torch, self.dist, self.part
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            check(lib.mfhn_dist_unique_id(uid.data_ptr()))
+        uid = uid.to(self.device)
+        dist.broadcast(uid, src=self._global_rank(0), group=self.group)
+        uid = uid.cpu().contiguous()
+        ip = np.array(self.import_peers, dtype=np.int32)
+        ioff = np.zeros(len(ip) + 1, dtype=np.int64)
+        for i, p in enumerate(self.import_peers):
+            ioff[i + 1] = ioff[i] + len(part.import_indices[p])
+        iidx = (np.concatenate([part.import_indices[p] for p in self.import_peers]).astype(np.int32) if len(ip)
+                else np.zeros(0, dtype=np.int32))
+        gp = np.array(self.ghost_peers, dtype=np.int32)
+        gb = np.array([part.ghost_ranges[p][0] for p in self.ghost_peers], dtype=np.int64)
+        ge = np.array([part.ghost_ranges[p][1] for p in self.ghost_peers], dtype=np.int64)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        desc = capi.DistDesc(rank=rank, world=world, unique_id=uid.data_ptr(), n_import_peers=len(ip), import_peers=ptr(ip),
+                             import_offsets=ptr(ioff), import_indices=ptr(iidx), n_ghost_peers=len(gp), ghost_peers=ptr(gp),
+                             ghost_begin=ptr(gb), ghost_end=ptr(ge), segments=(C.c_int64 * 4)(*self.seg))
+        h = C.c_void_p()
+        check(lib.mfhn_dist_create(op._h, C.byref(desc), C.byref(h)))
+        self._native = h
+
+    def __del__(self):
+        if getattr(self, "_native", None):
+            lib.mfhn_dist_destroy(self._native)
+            self._native = None
 
     # -- building blocks ---------------------------------------------------------
     def _global_rank(self, p):
@@ -120,6 +160,10 @@ class GhostExchange:
             self.local_apply(dst, src, s0, s3)
             self.compress_add(dst)
             return
+        if self._native is not None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            check(lib.mfhn_dist_vmult(self._native, dst.data_ptr(), src.data_ptr(), stream, 0))
+            return
         main = torch.cuda.current_stream(self.device)
         comm = self.comm_stream
         self._pack(src)
@@ -158,4 +202,7 @@ class GhostExchange:
 
     def launches_per_vmult(self):
         s0, s1, s2, s3 = self.seg
-        return int(s1 > s0) + int(s2 > s1) + int(s3 > s2) + 2 * len(self.import_peers)
+        cells = int(s1 > s0) + int(s2 > s1) + int(s3 > s2)
+        if self._native is not None:
+            return cells + 2 * int(self.part.n_import_indices() > 0)  # one pack + one unpack kernel
+        return cells + 2 * len(self.import_peers)

@@ -188,6 +188,35 @@ int mfhn_pack(int number, void *buffer, const void *vec, const int32_t *indices_
 int mfhn_unpack_add(int number, void *vec, const void *buffer, const int32_t *indices_dev,
                     int64_t n, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------
+ * Partitioned operator: the complete vmult of one rank -- ghost import, the three
+ * cell partitions, ghost compress -- issued by ONE call (pack / unpack kernels,
+ * NCCL send/recv groups on an internal communication stream, events).  This is
+ * CUDAWrappers::MatrixFree::cell_loop with its update_ghost_values /
+ * compress(add) (benchmark_03.h:348-353) for one process per GPU.  NCCL is
+ * resolved at run time (dlopen of libnccl.so.2).
+ * ------------------------------------------------------------------------ */
+typedef struct mfhn_dist_s *mfhn_dist;
+typedef struct
+{
+  int rank, world;
+  const void *unique_id;          /* 128 bytes from mfhn_dist_unique_id on rank 0, broadcast by the caller */
+  int n_import_peers;             /* peers that ghost entries owned here                                */
+  const int32_t *import_peers;    /* their ranks                                                        */
+  const int64_t *import_offsets;  /* [n_import_peers + 1] into import_indices                            */
+  const int32_t *import_indices;  /* local owned indices, grouped by peer                                */
+  int n_ghost_peers;              /* peers owning this rank's ghosts                                     */
+  const int32_t *ghost_peers;
+  const int64_t *ghost_begin;     /* per peer: its contiguous range inside the ghost section             */
+  const int64_t *ghost_end;
+  int64_t segments[4];            /* 0, end of interior A, end of interior B, n_cells (boundary cells last) */
+} mfhn_dist_desc;
+int mfhn_dist_unique_id(void *id128);
+int mfhn_dist_create(mfhn_op op, const mfhn_dist_desc *desc, mfhn_dist *out);
+void mfhn_dist_destroy(mfhn_dist d);
+int mfhn_dist_vmult(mfhn_dist d, void *dst, const void *src, void *cuda_stream, int zero_dst);
+int64_t mfhn_dist_launch_count(mfhn_dist d);
+
 /* Microbenchmarks used for the roofline denominators (bench.py). */
 int mfhn_bench_dfma(int number, int iters, double *tflops);
 
