@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--number", default="double", choices=["double", "float"])
     ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--hn-weight", type=float, default=1.0, help="partition weight of cells with hanging nodes (benchmark_02.cc:15-37)")
     ap.add_argument("--sweep", action="store_true", help="also time degrees 1..8 and the kernel variants (extra keys)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -246,10 +247,27 @@ def run():
         dst.zero_()
     with ClockSampler(local_rank) as clocks:
         total_ms, per = time_vmult(torch, op, dst, src, args.steps, args.warmup, barrier, graph)
+    rank_info = None
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+        # per-rank load: time of the rank-local cell loop alone (no exchange), cells, hanging-node cells
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            op.vmult_range(dst, src, 0, mf.n_cells)
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / 10, mf.n_cells, mf.n_cells_hn(), mf.n_cells - mf.n_interior_cells,
+                             mf.partitioner.n_ghost], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_info = {"local_cell_loop_ms": [round(float(a[0]), 4) for a in allr], "n_cells": [int(a[1]) for a in allr],
+                     "n_cells_hn": [int(a[2]) for a in allr], "n_boundary_cells": [int(a[3]) for a in allr],
+                     "n_ghost": [int(a[4]) for a in allr]}
+        dst.zero_()
     ms_per_step = total_ms / args.steps
     value = n_dofs_global / (ms_per_step * 1e-3) / 1e9
     if world > 1:
@@ -292,6 +310,8 @@ def run():
                        "kernel_ms_min_avg_max": [float(per.min()), float(per.mean()), float(per.max())],
                        "algorithmic_flops_per_launch": flops}
     out["clocks"] = clocks.summary()
+    if rank_info is not None:
+        out["ranks"] = rank_info
     out["config"] = {"workload": workload, "n_cells": int(prob["n_cells_global"]), "n_cells_hn": int(prob["n_cells_hn_global"]),
                      "n_dofs": int(n_dofs_global), "kernel": prob["kernel_name"], "partition": prob["partition"],
                      "l2": "inputs larger than L2 (vectors + index arrays >> 126 MB), no flush",

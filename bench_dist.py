@@ -20,7 +20,7 @@ def build_problem(mfhn, args, L, rank, world):
         from importlib import import_module
 
         distributed = import_module("dealii-matrixfree-hanging-nodes_b200.distributed")
-        rank_of_cell = tria.partition(world, 1.0)
+        rank_of_cell = tria.partition(world, args.hn_weight)
         dh = mfhn.DoFHandler(tria, args.degree, world, rank_of_cell)
         mf = mfhn.MatrixFree(dh, rank)
         mfhn.exchange_import_indices(mf.partitioner)
@@ -28,7 +28,7 @@ def build_problem(mfhn, args, L, rank, world):
         comm = distributed.GhostExchange(op)
         op.attach_communicator(comm)
         how = "one C-ABI call per vmult (NCCL groups issued from C++)" if comm._native is not None else "torch.distributed p2p groups"
-        partition = f"Morton (p4est-like) partition into {world} ranks, NCCL ghost import/compress overlapped with interior cells, {how}"
+        partition = f"Morton (p4est-like) partition into {world} ranks (hanging-node weight {args.hn_weight}), NCCL ghost import/compress overlapped with interior cells, {how}"
         launches = comm.launches_per_vmult()
 
     def fill_src(src):

@@ -882,7 +882,12 @@ int mfhn_dist_create(mfhn_op h, const mfhn_dist_desc *dd, mfhn_dist *out)
     CUDA_CHECK(cudaMemcpy(d->d_import_idx, dd->import_indices, d->n_import * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&d->d_send, std::max<size_t>(8, d->n_import * s)));
     CUDA_CHECK(cudaMalloc(&d->d_recv, std::max<size_t>(8, d->n_import * s)));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+    {
+      // highest priority: the NCCL kernels must not queue behind the blocks of an interior cell partition
+      int lo = 0, hi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi));
+    }
     for (auto &e : d->ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     NcclApi::Id id;
     std::memcpy(&id, dd->unique_id, sizeof(id));
