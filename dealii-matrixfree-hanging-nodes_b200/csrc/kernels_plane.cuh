@@ -293,10 +293,10 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
   {
     uint32_t idx[n * n];
 #pragma unroll
-    for (int j = 0; j < n * n; ++j) idx[j] = valid ? __ldg(ip + j * 32) : 0xffffffffu;
+    for (int j = 0; j < n * n; ++j) idx[j] = valid ? __ldg(ip + j * 32) : 0u; // every entry of a valid cell is a valid index
 #pragma unroll
     for (int j = 0; j < n * n; ++j)
-      u[j / n][j % n] = (idx[j] != 0xffffffffu) ? (TEX ? tex_fetch<Number>(p.src_tex, idx[j]) : __ldg(src + idx[j])) : Number(0);
+      u[j / n][j % n] = valid ? (TEX ? tex_fetch<Number>(p.src_tex, idx[j]) : __ldg(src + idx[j])) : Number(0);
   }
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
@@ -375,8 +375,7 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
 #pragma unroll
       for (int j = 0; j < n * n; ++j)
         {
-          const uint32_t g = __ldg(ip + j * 32);
-          if (g != 0xffffffffu) atomicAdd(dst + g, cellA[t * ps + j]);
+          atomicAdd(dst + __ldg(ip + j * 32), cellA[t * ps + j]);
         }
     }
 }

@@ -66,11 +66,11 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
 #pragma unroll
       for (int r = 0; r < RF; ++r)
 #pragma unroll
-        for (int x = 0; x < n; ++x) idx[r][x] = (valid && y0 + r < n) ? __ldg(ip + ((y0 + r) * n + x) * 32) : 0xffffffffu;
+        for (int x = 0; x < n; ++x) idx[r][x] = (valid && y0 + r < n) ? __ldg(ip + ((y0 + r) * n + x) * 32) : 0u;
 #pragma unroll
       for (int r = 0; r < RF; ++r)
 #pragma unroll
-        for (int x = 0; x < n; ++x) v[r][x] = (idx[r][x] != 0xffffffffu) ? __ldg(src + idx[r][x]) : Number(0);
+        for (int x = 0; x < n; ++x) v[r][x] = (valid && y0 + r < n) ? __ldg(src + idx[r][x]) : Number(0);
 #pragma unroll
       for (int r = 0; r < RF; ++r)
         if (y0 + r < n)
@@ -145,8 +145,7 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
 #pragma unroll
           for (int x = 0; x < n; ++x) g[x] = __ldg(ip + (y * n + x) * 32);
 #pragma unroll
-          for (int x = 0; x < n; ++x)
-            if (g[x] != 0xffffffffu) atomicAdd(dst + g[x], planeA[y * n + x]);
+          for (int x = 0; x < n; ++x) atomicAdd(dst + g[x], planeA[y * n + x]);
         }
     }
 }
