@@ -327,7 +327,7 @@ def run():
         out["no_constraints_gdofs"] = n_dofs_global / (float(np.mean(per_nc)) * 1e-3) / 1e9
         # the other kernels on the same problem, for the record
         variants = {}
-        for kname in ("plane", "qpoint", "separable"):
+        for kname in ("qpoint", "separable", "baseline"):
             try:
                 op.set_kernel(kname)
                 _, pk = time_vmult(torch, op, dst, src, 10, 3)
@@ -336,7 +336,20 @@ def run():
                 variants[kname] = str(e)
         op.set_kernel(args.kernel)
         out["kernel_variants_gdofs"] = variants
+        out["kernel_variants_note"] = ("baseline = restatement of the deal.II CUDAWrappers::MatrixFree design behind cuda/benchmark_03.cu "
+                                       "(one thread per DoF, per-q-point 3x3 inverse Jacobian + JxW from global memory, atomics), same box")
         out["fp64_fma_tflops_measured"] = mfhn.bench_fma("double", 20000)
+        # hanging-node strategies: cells in plain Morton order ("index" analogue) vs grouped by
+        # constraint flag inside Morton windows ("sorted" analogue, the reference's Categorize option; default)
+        mf_plain = mfhn.MatrixFree(prob["dh"], categorize=False)
+        op_plain = mfhn.LaplaceOperator(mf_plain, number=args.number, kernel=args.kernel)
+        _, p1 = time_vmult(torch, op_plain, dst, src, 10, 3)
+        op_plain.set_apply_constraints(False)
+        _, p0 = time_vmult(torch, op_plain, dst, src, 10, 3)
+        out["hn_strategies"] = {"sorted_overhead_percent": out["hn_overhead_percent"], "sorted_gdofs": value,
+                                "index_overhead_percent": 100.0 * (float(np.mean(p1)) / float(np.mean(p0)) - 1.0),
+                                "index_gdofs": n_dofs_global / (float(np.mean(p1)) * 1e-3) / 1e9}
+        del op_plain, mf_plain
 
     if not args.no_e2e and not args.minimal:
         # end to end through the host-vector entry point: H2D of src, kernel, D2H of dst every step

@@ -9,6 +9,7 @@
 #include "kernels_patch.cuh"
 #include "kernels_plane_smem.cuh"
 #include "dist.cuh"
+#include "kernels_baseline.cuh"
 #include "octree.hpp"
 
 #include <cuda_runtime.h>
@@ -250,6 +251,10 @@ struct Operator
   void *d_geom = nullptr;       // Number h[cell] or Number G[cell][6]
   PlaneLayout plane;            // warp-interleaved layout of the register-tiled kernel
   PatchLayout patch;            // sorted-unique / CSR layout of the patch kernel
+  // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use: 84 B per padded slot)
+  uint32_t *d_base_l2g = nullptr;
+  void *d_base_invjac = nullptr, *d_base_jxw = nullptr;
+  int base_pad = 0;
   std::vector<long long> segments;
   long long launches = 0;
   void *d_stage_src[2] = {nullptr, nullptr}, *d_stage_dst[2] = {nullptr, nullptr}; // device staging of the host-vector entry point (2 slots)
@@ -296,6 +301,9 @@ struct Operator
         cudaFree(d_stage_dst[i]);
       }
     for (auto &e : tex_cache) cudaDestroyTextureObject(e.second);
+    cudaFree(d_base_l2g);
+    cudaFree(d_base_invjac);
+    cudaFree(d_base_jxw);
     plane.free();
     patch.free();
   }
@@ -321,8 +329,48 @@ void launch_generic(const Operator &op, const CellLoopParams &p, cudaStream_t st
 }
 
 template <int n, typename Number>
+void launch_baseline(Operator &op, const CellLoopParams &p, cudaStream_t stream)
+{
+  using Cfg = BaselineCfg<n>;
+  if (!op.d_base_l2g)
+    {
+      const size_t slots = (size_t)std::max<long long>(op.n_cells, 1) * Cfg::pad;
+      CUDA_CHECK(cudaMalloc(&op.d_base_l2g, slots * sizeof(uint32_t)));
+      CUDA_CHECK(cudaMalloc(&op.d_base_invjac, slots * 9 * sizeof(Number)));
+      CUDA_CHECK(cudaMalloc(&op.d_base_jxw, slots * sizeof(Number)));
+      op.base_pad = Cfg::pad;
+      if (op.n_cells > 0)
+        baseline_setup_kernel<n, Number><<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(
+          op.d_base_l2g, (Number *)op.d_base_invjac, (Number *)op.d_base_jxw, op.d_idx, (const Number *)op.d_geom, op.n_cells, Cfg::pad);
+      CUDA_CHECK(cudaGetLastError());
+    }
+  BaselineParams b;
+  b.local_to_global   = op.d_base_l2g;
+  b.inv_jacobian      = op.d_base_invjac;
+  b.JxW               = op.d_base_jxw;
+  b.masks             = p.masks;
+  b.src               = p.src;
+  b.dst               = p.dst;
+  b.n_cells           = op.n_cells;
+  b.cell_begin        = p.cell_begin;
+  b.cell_end          = p.cell_end;
+  b.pad               = Cfg::pad;
+  b.apply_constraints = p.apply_constraints;
+  const long long nc  = p.cell_end - p.cell_begin;
+  if (nc <= 0) return;
+  baseline_kernel<n, Number><<<(unsigned)((nc + Cfg::cpb - 1) / Cfg::cpb), Cfg::n3 * Cfg::cpb, 0, stream>>>(b);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int n, typename Number>
 void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
 {
+  if (kernel == MFHN_KERNEL_BASELINE)
+    {
+      launch_baseline<n, Number>(op, p, stream);
+      ++op.launches;
+      return;
+    }
   if (kernel == MFHN_KERNEL_PATCH)
     launch_patch<n, Number>(op.patch, p, op.device, stream);
   else if (kernel == MFHN_KERNEL_PLANE && plane_supported(n))
@@ -366,7 +414,8 @@ int resolve_kernel(const Operator &op)
     throw NotImplemented("MFHN_KERNEL_PATCH is not available for this degree");
   if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
-  if (kernel == MFHN_KERNEL_BASELINE) throw NotImplemented("MFHN_KERNEL_BASELINE is not built yet");
+  if (kernel == MFHN_KERNEL_BASELINE && op.geometry_type != MFHN_GEOM_CARTESIAN)
+    throw InvalidArgument("the baseline kernel is set up for Cartesian cells");
   return kernel;
 }
 

@@ -50,7 +50,7 @@ def test_cpp_setup_reproduces_golden_bit_exact(path, mfhn):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", FIXTURES, ids=os.path.basename)
-@pytest.mark.parametrize("kernel", ["qpoint", "separable", "plane", "patch"])
+@pytest.mark.parametrize("kernel", ["qpoint", "separable", "plane", "patch", "baseline"])
 def test_cuda_reproduces_golden(path, kernel, mfhn):
     import torch
 

@@ -44,7 +44,7 @@ def _run(mfhn, mf, x, number, kernel, apply_constraints=True):
     return dst.cpu().numpy().astype(np.float64), op
 
 
-KERNELS = ["qpoint", "separable", "plane", "patch"]
+KERNELS = ["qpoint", "separable", "plane", "patch", "baseline"]
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
