@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--hn-weight", type=float, default=1.0, help="partition weight of cells with hanging nodes (benchmark_02.cc:15-37)")
     ap.add_argument("--sweep", action="store_true", help="also time degrees 1..8 and the kernel variants (extra keys)")
+    ap.add_argument("--stages", action="store_true", help="the reference's DG (SC) / CG (SC) decomposition and eta (benchmark_01.cc:189-220)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="timed loop only (for profiler runs)")
@@ -325,6 +326,10 @@ def run():
         op.set_apply_constraints(True)
         out["hn_overhead_percent"] = 100.0 * (float(np.mean(per)) / float(np.mean(per_nc)) - 1.0)
         out["no_constraints_gdofs"] = n_dofs_global / (float(np.mean(per_nc)) * 1e-3) / 1e9
+        # cost of a cell with hanging nodes relative to a regular cell: eta of benchmark_01.cc:179-187 (CG (SC): t4, t5)
+        n_hn, n_all = int(prob["n_cells_hn_global"]), int(prob["n_cells_global"])
+        t_n, t_hn = float(np.mean(per_nc)), float(np.mean(per))
+        out["eta5"] = max((t_hn / (t_n / n_all) - (n_all - n_hn)) / n_hn, 1.0) if n_hn else 1.0
         # the other kernels on the same problem, for the record
         variants = {}
         for kname in ("qpoint", "separable", "baseline"):
@@ -416,6 +421,12 @@ def run():
         from bench_dist import degree_sweep
 
         out["degree_sweep"] = degree_sweep(mfhn, torch, args, time_vmult)
+    if args.stages and world == 1 and rank == 0:
+        from bench_dist import stage_benchmarks
+
+        del op, src, dst
+        torch.cuda.empty_cache()
+        out["stages"] = stage_benchmarks(mfhn, torch, args, L, time_vmult)
 
     if world > 1:
         dist.destroy_process_group()

@@ -69,3 +69,62 @@ def degree_sweep(mfhn, torch, args, time_vmult):
             del op, src, dst
             torch.cuda.empty_cache()
     return res
+
+
+def stage_benchmarks(mfhn, torch, args, L, time_vmult):
+    """The reference's decomposition (benchmark_01.cc:189-220) on the GPU: "DG (SC)" = every cell owns private
+    DoFs (contiguous cell-local gather / scatter, benchmark_01.h:639-677) with and without the interpolation
+    (t2, t3, eta3); "CG (SC)" = the real operator (t4, t5, eta5); and the interpolation alone on cell-local
+    values (benchmark_00_likwid.cc:56-59)."""
+    import numpy as np
+
+    tria = mfhn.Triangulation(args.geometry, L, "p4est")
+    dh = mfhn.DoFHandler(tria, args.degree)
+    mf = mfhn.MatrixFree(dh)
+    n3 = (args.degree + 1) ** 3
+    n_hn, n_all = mf.n_cells_hn(), mf.n_cells
+
+    def eta(t_n, t_hn):
+        return max((t_hn / (t_n / n_all) - (n_all - n_hn)) / n_hn, 1.0) if n_hn else 1.0
+
+    res = {"n_cells": n_all, "n_cells_hn": n_hn}
+    # CG (SC)
+    op = mfhn.LaplaceOperator(mf, number=args.number)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.fill_(1.0)  # benchmark_01.h:510-511
+    op.set_apply_constraints(False)
+    _, t4 = time_vmult(torch, op, dst, src, 10, 3)
+    op.set_apply_constraints(True)
+    _, t5 = time_vmult(torch, op, dst, src, 10, 3)
+    res.update(t4_ms=float(t4.mean()), t5_ms=float(t5.mean()), eta5=eta(float(t4.mean()), float(t5.mean())))
+    # the interpolation alone
+    vals = torch.ones(mf.n_cells * n3, dtype=src.dtype, device=src.device)
+    for _ in range(3):
+        op.apply_hanging_node_constraints(vals, False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        op.apply_hanging_node_constraints(vals, False)
+    e1.record()
+    torch.cuda.synchronize()
+    res["hn_kernel_alone_ms"] = e0.elapsed_time(e1) / 10
+    del op, src, dst, vals
+    torch.cuda.empty_cache()
+    # DG (SC): private DoFs per cell
+    class _DG:
+        pass
+
+    dg = _DG()
+    dg.degree, dg.n_cells, dg.h, dg.masks = mf.degree, mf.n_cells, mf.h, mf.masks
+    dg.dof_indices = np.arange(mf.n_cells * n3, dtype=np.uint32).reshape(mf.n_cells, n3)
+    dg.n_interior_cells = dg.n_interior_a = mf.n_cells
+    dg.partitioner = mfhn.Partitioner(0, 1, (0, mf.n_cells * n3), np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64))
+    op = mfhn.LaplaceOperator(dg, number=args.number)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.fill_(1.0)
+    op.set_apply_constraints(False)
+    _, t2 = time_vmult(torch, op, dst, src, 10, 3)
+    op.set_apply_constraints(True)
+    _, t3 = time_vmult(torch, op, dst, src, 10, 3)
+    res.update(t2_ms=float(t2.mean()), t3_ms=float(t3.mean()), eta3=eta(float(t2.mean()), float(t3.mean())))
+    return res
