@@ -14,6 +14,7 @@ from . import _capi as capi
 from ._capi import MfhnError, NotImplementedMfhn
 from .api import (DoFHandler, LaplaceOperator, MatrixFree, Partitioner, Triangulation, bench_fma,
                   exchange_import_indices)
+from .solvers import solve_cg
 
 __all__ = ["capi", "MfhnError", "NotImplementedMfhn", "Triangulation", "DoFHandler", "MatrixFree",
-           "Partitioner", "LaplaceOperator", "bench_fma", "exchange_import_indices"]
+           "Partitioner", "LaplaceOperator", "bench_fma", "exchange_import_indices", "solve_cg"]

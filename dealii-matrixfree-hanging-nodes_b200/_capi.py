@@ -88,6 +88,7 @@ SIGNATURES = {
     "mfhn_op_vmult_range": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64]),
     "mfhn_op_vmult_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "mfhn_op_vmult_host_slot": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "mfhn_op_diagonal": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mfhn_op_set_apply_constraints": (c_int, [c_void_p, c_int]),
     "mfhn_op_set_kernel": (c_int, [c_void_p, c_int]),
     "mfhn_op_apply_hn": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -320,6 +320,17 @@ class LaplaceOperator:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(lib.mfhn_op_vmult_range(self._h, dst.data_ptr(), src.data_ptr(), stream, cell_begin, cell_end))
 
+    def compute_diagonal(self):
+        """Diagonal of the operator as a vector (hanging entries are zero).  Extension for a
+        point-Jacobi preconditioner (BASELINE.json config 5); no counterpart in the reference."""
+        torch = _torch()
+        diag = self.initialize_dof_vector()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(lib.mfhn_op_diagonal(self._h, diag.data_ptr(), stream))
+        if self._comm is not None:
+            self._comm.compress_add(diag)
+        return diag
+
     def apply_hanging_node_constraints(self, cell_values, transpose: bool):
         """FEEvaluationHangingNodesFactory::apply on [n_cells, (k+1)^3] values
         (benchmark_00_likwid.cc:56-59)."""

@@ -106,7 +106,11 @@ __host__ __device__ constexpr int generic_n_arrays()
   return VARIANT == GV_QPOINT_METRIC ? 4 : 2;
 }
 
-template <int n, typename Number, int VARIANT>
+// DIAG = true computes the diagonal of the operator instead of applying it: for every local
+// DoF j the cell operator (with the hanging-node interpolation and its transpose) is applied to
+// the unit vector e_j and entry j of the result is added to dst -- (k+1)^3 cell applications per
+// cell, a one-time setup cost of a point-Jacobi preconditioner.
+template <int n, typename Number, int VARIANT, bool DIAG = false>
 __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(const CellLoopParams p)
 {
   using Cfg        = GenericCfg<n>;
@@ -139,9 +143,21 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
       const uint32_t *ip = p.idx + cell * (long long)(n * n * n) + l;
 #pragma unroll
       for (int z = 0; z < n; ++z) gidx[z] = ip[z * n * n];
+      if (p.apply_constraints) mask = p.masks[cell];
+    }
+#pragma unroll 1
+  for (int unit = 0; unit < (DIAG ? n * n * n : 1); ++unit)
+  {
+  if (DIAG)
+    {
+      __syncthreads();
+#pragma unroll
+      for (int z = 0; z < n; ++z) A0[bz + z * sz] = (l + n * n * z == unit) ? Number(1) : Number(0);
+    }
+  else if (valid)
+    {
 #pragma unroll
       for (int z = 0; z < n; ++z) A0[bz + z * sz] = src[gidx[z]];
-      if (p.apply_constraints) mask = p.masks[cell];
     }
   const bool any_hn = __syncthreads_or(mask != 0);
   unsigned face = 0, edge = 0, childbits = 0;
@@ -337,7 +353,9 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
   if (valid)
     {
 #pragma unroll
-      for (int z = 0; z < n; ++z) atomicAdd(dst + gidx[z], A0[bz + z * sz]);
+      for (int z = 0; z < n; ++z)
+        if (!DIAG || l + n * n * z == unit) atomicAdd(dst + gidx[z], A0[bz + z * sz]);
     }
+  } // unit vectors
 }
 } // namespace mfhn

@@ -310,7 +310,7 @@ struct Operator
 };
 
 // ---------------------------------------------------------------------------
-template <int n, typename Number, int V>
+template <int n, typename Number, int V, bool DIAG = false>
 void launch_generic(const Operator &op, const CellLoopParams &p, cudaStream_t stream)
 {
   using Cfg           = GenericCfg<n>;
@@ -318,14 +318,41 @@ void launch_generic(const Operator &op, const CellLoopParams &p, cudaStream_t st
   static bool attr[64] = {};
   if (smem > 48 * 1024 && !attr[op.device])
     {
-      CUDA_CHECK(cudaFuncSetAttribute(generic_cell_kernel<n, Number, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaFuncSetAttribute(generic_cell_kernel<n, Number, V, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr[op.device] = true;
     }
   const long long nc = p.cell_end - p.cell_begin;
   if (nc <= 0) return;
   const unsigned grid = (unsigned)((nc + Cfg::cpb - 1) / Cfg::cpb);
-  generic_cell_kernel<n, Number, V><<<grid, Cfg::threads, smem, stream>>>(p);
+  generic_cell_kernel<n, Number, V, DIAG><<<grid, Cfg::threads, smem, stream>>>(p);
   CUDA_CHECK(cudaGetLastError());
+}
+
+// diagonal of the operator (for point-Jacobi): Cartesian cells through the separable form, affine through the q-point form
+template <int n, typename Number>
+void launch_diagonal_n(Operator &op, const CellLoopParams &p, cudaStream_t stream)
+{
+  if (op.geometry_type == MFHN_GEOM_AFFINE)
+    launch_generic<n, Number, GV_QPOINT_METRIC, true>(op, p, stream);
+  else
+    launch_generic<n, Number, GV_SEPARABLE, true>(op, p, stream);
+  ++op.launches;
+}
+template <typename Number>
+void launch_diagonal(Operator &op, const CellLoopParams &p, cudaStream_t stream)
+{
+  switch (op.degree)
+    {
+      case 1: launch_diagonal_n<2, Number>(op, p, stream); break;
+      case 2: launch_diagonal_n<3, Number>(op, p, stream); break;
+      case 3: launch_diagonal_n<4, Number>(op, p, stream); break;
+      case 4: launch_diagonal_n<5, Number>(op, p, stream); break;
+      case 5: launch_diagonal_n<6, Number>(op, p, stream); break;
+      case 6: launch_diagonal_n<7, Number>(op, p, stream); break;
+      case 7: launch_diagonal_n<8, Number>(op, p, stream); break;
+      case 8: launch_diagonal_n<9, Number>(op, p, stream); break;
+      default: throw InvalidArgument("unsupported degree");
+    }
 }
 
 template <int n, typename Number>
@@ -762,6 +789,27 @@ int mfhn_op_vmult_host_slot(mfhn_op h, void *dst_host, const void *src_host, voi
 int mfhn_op_vmult_host(mfhn_op h, void *dst_host, const void *src_host, void *stream, int zero_dst)
 {
   return mfhn_op_vmult_host_slot(h, dst_host, src_host, stream, zero_dst, 0);
+}
+int mfhn_op_diagonal(mfhn_op h, void *diag, void *stream)
+{
+  return guard([&] {
+    if (!h || !diag) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    CellLoopParams p;
+    p.idx               = op.d_idx;
+    p.masks             = op.d_masks;
+    p.geom              = op.d_geom;
+    p.src               = diag; // unused
+    p.dst               = diag;
+    p.cell_begin        = 0;
+    p.cell_end          = op.n_cells;
+    p.apply_constraints = op.apply_constraints;
+    if (op.number == MFHN_F64)
+      launch_diagonal<double>(op, p, static_cast<cudaStream_t>(stream));
+    else
+      launch_diagonal<float>(op, p, static_cast<cudaStream_t>(stream));
+  });
 }
 int mfhn_op_set_apply_constraints(mfhn_op h, int v)
 {

@@ -162,6 +162,11 @@ int mfhn_op_vmult_host(mfhn_op op, void *dst_host, const void *src_host, void *c
 int mfhn_op_vmult_host_slot(mfhn_op op, void *dst_host, const void *src_host, void *cuda_stream,
                             int zero_dst, int slot);
 
+/* diag += diagonal of the operator (device vector of n_owned + n_ghost entries; ghost entries
+ * hold the contributions to peers' DoFs and must be compressed like a vmult result).  Extension
+ * for a point-Jacobi preconditioner (BASELINE.json config 5); the reference has no counterpart. */
+int mfhn_op_diagonal(mfhn_op op, void *diag, void *cuda_stream);
+
 /* Change the apply_constraints switch / kernel of an existing operator. */
 int mfhn_op_set_apply_constraints(mfhn_op op, int apply_constraints);
 int mfhn_op_set_kernel(mfhn_op op, int kernel);

@@ -243,3 +243,38 @@ def test_host_vector_entry_point(mfhn):
         assert np.abs(hd.numpy() - 2 * ref).max() / np.abs(ref).max() < 1e-12
     with pytest.raises(mfhn.MfhnError):
         op.vmult_host(hd, hs, slot=2)
+
+
+@pytest.mark.parametrize("geo,L,k", [("annulus", 5, 2), ("quadrant", 3, 4), ("quadrant", 2, 7)])
+def test_diagonal_and_jacobi_cg(mfhn, geo, L, k):
+    """Extension (BASELINE.json config 5; the reference has no solver): the operator diagonal equals
+    diag(C^T K C) of the general-purpose oracle, and point-Jacobi CG solves a consistent system."""
+    import torch
+
+    t = mesh.create(geo, L, "serial")
+    lay = dofs.setup(t, k)
+    O1 = operators.GeneralOperator(t, lay)
+    A = (O1.C.T @ O1.K @ O1.C).tocsr()
+    tria = mfhn.Triangulation(geo, L, "serial")
+    dh = mfhn.DoFHandler(tria, k)
+    mf = mfhn.MatrixFree(dh)
+    op = mfhn.LaplaceOperator(mf)
+    diag = op.compute_diagonal()
+    ref = A.diagonal()
+    assert np.abs(diag.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-12
+    assert (diag.cpu().numpy()[O1.is_hanging] == 0).all()
+    # consistent right-hand side b = A x*, x* random on the live DoFs
+    live = ~O1.is_hanging
+    xs = np.zeros(lay.n_dofs)
+    xs[live] = np.random.default_rng(5).uniform(-1, 1, live.sum())
+    b = torch.from_numpy(A @ xs).cuda()
+    x = op.initialize_dof_vector()
+    its_jacobi, hist = mfhn.solve_cg(op, x, b, diag=diag, rel_tol=1e-10, max_iter=2000)
+    assert hist[-1] <= 1e-10 * hist[0] and its_jacobi < 2000
+    xn = x.cpu().numpy()
+    assert np.abs(A @ xn - A @ xs).max() <= 1e-8 * np.abs(A @ xs).max()
+    d = (xn - xs)[live]
+    assert np.abs(d - d.mean()).max() < 1e-6 * np.abs(xs).max()  # equal up to the constant null space
+    x2 = op.initialize_dof_vector()
+    its_plain, _ = mfhn.solve_cg(op, x2, b, diag=None, rel_tol=1e-10, max_iter=4000)
+    assert its_jacobi <= its_plain  # the preconditioner pays off on the graded mesh
