@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
   unsigned hn_face, hn_edge, hn_cb;
   decode_mask_kernel_axes(mask, hn_face, hn_edge, hn_cb);
 
-  // ---- P0: gather, RF rows in flight -------------------------------------------------
+  // ---- P0: gather, RF rows in flight.  Warps without a constrained cell fuse the X sweep into the
+  // gather (rows go straight from registers to p, q); the others stage u in A for the interpolation.
 #pragma unroll 1
   for (int y0 = 0; y0 < n; y0 += RF)
     {
@@ -75,30 +76,45 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
       for (int r = 0; r < RF; ++r)
         if (y0 + r < n)
           {
+            if (any_hn)
+              {
 #pragma unroll
-            for (int x = 0; x < n; ++x) planeA[(y0 + r) * n + x] = v[r][x];
+                for (int x = 0; x < n; ++x) planeA[(y0 + r) * n + x] = v[r][x];
+              }
+            else
+              {
+                Number pr[n], qr[n];
+                apply_MK<n>(v[r], pr, qr);
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+                  {
+                    planeA[(y0 + r) * n + x] = pr[x];
+                    planeB[(y0 + r) * n + x] = qr[x];
+                  }
+              }
           }
     }
   if (any_hn)
     {
       __syncwarp();
       hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t);
-    }
-  // ---- P1: X sweep on the rows, Y sweep on the columns of the private plane ----------
+      // ---- P1: X sweep on the rows of the private plane ---------------------------------
 #pragma unroll 1
-  for (int y = 0; y < n; ++y)
-    {
-      Number u[n], pr[n], qr[n];
-#pragma unroll
-      for (int x = 0; x < n; ++x) u[x] = planeA[y * n + x];
-      apply_MK<n>(u, pr, qr);
-#pragma unroll
-      for (int x = 0; x < n; ++x)
+      for (int y = 0; y < n; ++y)
         {
-          planeA[y * n + x] = pr[x];
-          planeB[y * n + x] = qr[x];
+          Number u[n], pr[n], qr[n];
+#pragma unroll
+          for (int x = 0; x < n; ++x) u[x] = planeA[y * n + x];
+          apply_MK<n>(u, pr, qr);
+#pragma unroll
+          for (int x = 0; x < n; ++x)
+            {
+              planeA[y * n + x] = pr[x];
+              planeB[y * n + x] = qr[x];
+            }
         }
     }
+  // ---- P1: Y sweep on the columns of the private plane ---------------------------------
 #pragma unroll 1
   for (int x = 0; x < n; ++x)
     {
