@@ -62,7 +62,6 @@ struct PlaneParams
   const uint32_t *pidx; // [n_batches][n*n][32]
   const uint8_t *masks; // [n_cells]
   const void *h;        // Number[n_cells]
-  const void *w0;       // Number[n*n] subface interpolation matrix (global copy)
   const void *src;
   void *dst;
   long long cell_begin, cell_end, batch_begin, batch_end;
@@ -386,16 +385,13 @@ struct PlaneLayout
   int n = 0;
   long long n_cells = 0, n_batches = 0;
   uint32_t *d_pidx = nullptr;
-  void *d_w0       = nullptr;
 
   void free()
   {
     cudaFree(d_pidx);
-    cudaFree(d_w0);
     d_pidx = nullptr;
-    d_w0   = nullptr;
   }
-  void build(int n_, int number, long long n_cells_, const uint32_t *idx, const double *w0);
+  void build(int n_, long long n_cells_, const uint32_t *idx);
 };
 
 template <int n, typename Number>
@@ -415,7 +411,6 @@ void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.pidx              = L.d_pidx;
   p.masks             = cp.masks;
   p.h                 = cp.geom;
-  p.w0                = L.d_w0;
   p.src               = cp.src;
   p.dst               = cp.dst;
   p.cell_begin        = cp.cell_begin;

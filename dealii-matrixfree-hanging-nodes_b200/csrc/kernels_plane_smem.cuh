@@ -181,7 +181,6 @@ void launch_plane_smem(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.pidx              = L.d_pidx;
   p.masks             = cp.masks;
   p.h                 = cp.geom;
-  p.w0                = L.d_w0;
   p.src               = cp.src;
   p.dst               = cp.dst;
   p.cell_begin        = cp.cell_begin;

@@ -104,7 +104,7 @@ T *to_device(const std::vector<T> &h)
 }
 } // namespace
 
-void PlaneLayout::build(int n_, int number, long long n_cells_, const uint32_t *idx, const double *w0)
+void PlaneLayout::build(int n_, long long n_cells_, const uint32_t *idx)
 {
   n               = n_;
   n_cells         = n_cells_;
@@ -123,16 +123,6 @@ void PlaneLayout::build(int n_, int number, long long n_cells_, const uint32_t *
         for (int j = 0; j < n2; ++j) p[((size_t)batch * n2 + j) * 32 + slot * n + t] = idx[c * n3 + t + (long long)n * j];
     }
   d_pidx = to_device(p);
-  if (number == MFHN_F64)
-    {
-      std::vector<double> w(w0, w0 + n2);
-      d_w0 = to_device(w);
-    }
-  else
-    {
-      std::vector<float> w(w0, w0 + n2);
-      d_w0 = to_device(w);
-    }
 }
 
 template <int n, typename Number>
@@ -155,55 +145,53 @@ static int patch_slot_n(int n, int s, int j)
     }
 }
 
-void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *idx, const std::vector<long long> &segments)
+void PatchLayout::build(int n_, int number_, long long n_cells_, const uint32_t *idx)
 {
-  n      = n_;
-  number = number_;
-  const int cpw = 32 / n, P = cpw, n3 = n * n * n, ent_stride = P * n3;
-  // patches never straddle a segment boundary
-  patch_cell_begin.clear();
-  for (size_t sgm = 0; sgm < segments.size(); ++sgm)
-    {
-      const long long b = segments[sgm], e = sgm + 1 < segments.size() ? segments[sgm + 1] : n_cells;
-      for (long long c = b; c < e; c += P) patch_cell_begin.push_back(c);
-    }
-  n_patches = (long long)patch_cell_begin.size();
-  patch_cell_begin.push_back(n_cells);
-  std::vector<uint32_t> uidx((size_t)std::max<long long>(n_patches, 1) * ent_stride, 0u);
-  std::vector<uint16_t> ent((size_t)std::max<long long>(n_patches, 1) * ent_stride, 0);
-  std::vector<PatchInfo> info(std::max<long long>(n_patches, 1));
+  n       = n_;
+  number  = number_;
+  n_cells = n_cells_;
+  const int cpw = 32 / n, n2 = n * n, n3 = n2 * n, ent_stride = cpw * n3;
+  const int rounds = (ent_stride + 31) / 32, u_stride = rounds * 32;
+  n_patches = (n_cells + cpw - 1) / cpw;
+  const size_t np = (size_t)std::max<long long>(n_patches, 1);
+  std::vector<uint32_t> uidx(np * u_stride, 0u);
+  std::vector<uint16_t> lidx(np * n2 * 32, 0);
+  std::vector<uint16_t> ent(np * ent_stride, 0);
+  std::vector<PatchInfo> info(np);
   long long total = 0;
 #pragma omp parallel reduction(+ : total)
   {
-    std::vector<std::pair<uint32_t, uint16_t>> pairs;
+    struct Entry { uint32_t g; uint16_t slot, lpos; }; // lpos = plane slot * 32 + lane
+    std::vector<Entry> entries;
     struct Group { uint32_t g; int first, count; };
     std::vector<Group> groups;
 #pragma omp for schedule(dynamic, 64)
     for (long long pt = 0; pt < n_patches; ++pt)
       {
-        const long long cb = patch_cell_begin[pt];
-        // a patch ends at the next patch start (segment ends are patch starts too)
-        const int nc = (int)std::min<long long>(P, patch_cell_begin[pt + 1] - cb);
-        pairs.clear();
+        const long long cb = pt * cpw;
+        const int nc       = (int)std::min<long long>(cpw, n_cells - cb);
+        entries.clear();
         for (int s = 0; s < nc; ++s)
           for (int j = 0; j < n3; ++j)
             {
+              const int x = j % n, y = (j / n) % n, z = j / n2;
               const int slot = number == MFHN_F64 ? patch_slot_n<double>(n, s, j) : patch_slot_n<float>(n, s, j);
-              pairs.emplace_back(idx[(cb + s) * n3 + j], (uint16_t)slot);
+              // thread t = x of cell s sits in lane s n + x; its plane slot is y + n z (kernel axes (X,Y,Z) = (y,z,x))
+              entries.push_back(Entry{idx[(cb + s) * n3 + j], (uint16_t)slot, (uint16_t)((y + n * z) * 32 + s * n + x)});
             }
-        std::sort(pairs.begin(), pairs.end());
+        std::sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.g < b.g; });
         groups.clear();
-        for (int i = 0; i < (int)pairs.size();)
+        for (int i = 0; i < (int)entries.size();)
           {
             int j = i;
-            while (j < (int)pairs.size() && pairs[j].first == pairs[i].first) ++j;
-            // multiplicities other than 1, 2, 4, 8 are split (3 = 2 + 1, ...): such a DoF is
-            // listed more than once, i.e. read twice and sent two REDs
+            while (j < (int)entries.size() && entries[j].g == entries[i].g) ++j;
+            // multiplicities other than 1, 2, 4, 8 are split (3 = 2 + 1, ...): such a DoF is listed more
+            // than once, i.e. read twice and sent two REDs
             int first = i, left = j - i;
             while (left > 0)
               {
                 const int piece = left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
-                groups.push_back(Group{pairs[i].first, first, piece});
+                groups.push_back(Group{entries[i].g, first, piece});
                 first += piece;
                 left -= piece;
               }
@@ -212,13 +200,13 @@ void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *
         // classes by multiplicity (uniform trip counts), ascending address inside a class
         std::stable_sort(groups.begin(), groups.end(), [](const Group &a, const Group &b) { return a.count < b.count; });
         PatchInfo &pi = info[pt];
-        pi.cell_begin = cb;
-        pi.n_cells    = nc;
+        pi.n_unique   = (unsigned short)groups.size();
         pi.pad[0] = pi.pad[1] = pi.pad[2] = 0;
         for (int m = 0; m < N_CLASSES; ++m) pi.count[m] = 0;
         for (const Group &g : groups) ++pi.count[g.count == 1 ? 0 : g.count == 2 ? 1 : g.count == 4 ? 2 : 3];
-        uint32_t *u = uidx.data() + pt * ent_stride;
-        uint16_t *e = ent.data() + pt * ent_stride;
+        uint32_t *u = uidx.data() + pt * u_stride;
+        uint16_t *l = lidx.data() + pt * (size_t)n2 * 32;
+        uint16_t *e = ent.data() + pt * (size_t)ent_stride;
         size_t gi = 0;
         int ebase = 0;
         for (int ci = 0; ci < N_CLASSES; ++ci)
@@ -227,17 +215,24 @@ void PatchLayout::build(int n_, int number_, long long n_cells, const uint32_t *
             for (int i = 0; i < cnt; ++i, ++gi)
               {
                 u[gi] = groups[gi].g;
-                for (int q = 0; q < m; ++q) e[ebase + q * cnt + i] = pairs[groups[gi].first + q].second;
+                for (int q = 0; q < m; ++q)
+                  {
+                    const Entry &en        = entries[groups[gi].first + q];
+                    e[ebase + q * cnt + i] = en.slot;
+                    l[en.lpos]             = (uint16_t)gi;
+                  }
               }
             ebase += m * cnt;
           }
+        for (size_t i = groups.size(); i < (size_t)u_stride; ++i) u[i] = groups.empty() ? 0u : groups.back().g; // padding: valid address
         total += (long long)groups.size();
       }
   }
   unique_per_cell = n_cells > 0 ? (double)total / (double)n_cells : 0;
-  index_bytes     = total * 4 + n_cells * (long long)n3 * 2 + n_patches * (long long)sizeof(PatchInfo);
+  index_bytes     = total * 4 + n_patches * (long long)n2 * 64 + n_cells * (long long)n3 * 2 + n_patches * (long long)sizeof(PatchInfo);
   d_patches       = to_device(info);
   d_uidx          = to_device(uidx);
+  d_lidx          = to_device(lidx);
   d_ent           = to_device(ent);
 }
 
@@ -439,6 +434,8 @@ int resolve_kernel(const Operator &op)
     throw InvalidArgument("affine geometry requires MFHN_KERNEL_QPOINT");
   if (kernel == MFHN_KERNEL_PATCH && !plane_supported(op.degree + 1))
     throw NotImplemented("MFHN_KERNEL_PATCH is not available for this degree");
+  if (kernel == MFHN_KERNEL_PATCH && op.patch.d_uidx == nullptr)
+    throw InvalidArgument("the patch layout is built only when the operator is created with MFHN_KERNEL_PATCH");
   if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
   if (kernel == MFHN_KERNEL_BASELINE && op.geometry_type != MFHN_GEOM_CARTESIAN)
@@ -537,8 +534,7 @@ Operator *op_create(const mfhn_op_desc &d)
     }
   if (d.geometry_type == MFHN_GEOM_CARTESIAN)
     {
-      const Shape1D sh = make_shape(d.degree);
-      op->plane.build(n, d.number, d.n_cells, d.dof_indices, sh.W[0].data());
+      op->plane.build(n, d.n_cells, d.dof_indices);
       op->segments.assign(1, 0);
       if (d.segments)
         {
@@ -547,7 +543,7 @@ Operator *op_create(const mfhn_op_desc &d)
           for (int i = 1; i < d.n_segments; ++i)
             if (d.segments[i] < d.segments[i - 1] || d.segments[i] > d.n_cells) throw InvalidArgument("segments must be ascending");
         }
-      if (plane_supported(n)) op->patch.build(n, d.number, d.n_cells, d.dof_indices, op->segments);
+      if (plane_supported(n) && (d.kernel == MFHN_KERNEL_PATCH || std::getenv("MFHN_BUILD_PATCH"))) op->patch.build(n, d.number, d.n_cells, d.dof_indices);
     }
   resolve_kernel(*op);
   return op.release();
