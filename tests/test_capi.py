@@ -74,7 +74,7 @@ def test_matrix_free_host_layout(mfhn):
     # cells are visited along the Morton curve (MatrixFree is free to reorder its batches)
     pos = tria.morton_position()
     assert (np.diff(pos[mf.cell_ids]) > 0).all()
-    # Categorize (benchmark_01.h:258-284): same cells, hanging-node cells grouped inside Morton windows
+    # Categorize (benchmark_01.h:258-284): same cells, grouped by constraint mask inside Morton windows
     mfc = mfhn.MatrixFree(dh)
     assert sorted(mfc.cell_ids) == sorted(mf.cell_ids) and mfc.n_cells_hn() == mf.n_cells_hn()
-    assert np.abs(pos[mfc.cell_ids] - np.arange(mf.n_cells)).max() < 240
+    assert np.abs(pos[mfc.cell_ids] - np.arange(mf.n_cells)).max() < 960
