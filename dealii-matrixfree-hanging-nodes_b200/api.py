@@ -257,6 +257,13 @@ class LaplaceOperator:
         kern = capi.KERNELS[kernel]
         cuts = sorted({0, matrix_free.n_interior_a, matrix_free.n_interior_cells} - {matrix_free.n_cells})
         self._segments = np.array(cuts, dtype=np.int64)
+        # the C ABI trusts the sizes it is given: check the host arrays before handing over raw pointers
+        n3 = (matrix_free.degree + 1) ** 3
+        for name, arr, shape, dtype in (("dof_indices", matrix_free.dof_indices, (matrix_free.n_cells, n3), np.uint32),
+                                        ("masks", matrix_free.masks, (matrix_free.n_cells,), np.uint8),
+                                        ("h", matrix_free.h, (matrix_free.n_cells,), np.float64)):
+            if arr.shape != shape or arr.dtype != dtype or not arr.flags["C_CONTIGUOUS"]:
+                raise capi.MfhnError(1, f"{name} must be a C-contiguous {np.dtype(dtype).name} array of shape {shape}")
         if geometry is None:
             gtype, geom = capi.GEOM_CARTESIAN, matrix_free.h
         else:  # (n_cells, 3, 3) Jacobians
