@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--number", default="double", choices=["double", "float"])
     ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="partitioned runs: NCCL ghost import/compress (default) or peer-memory access of the owners' vectors")
     ap.add_argument("--hn-weight", type=float, default=1.0, help="partition weight of cells with hanging nodes (benchmark_02.cc:15-37)")
     ap.add_argument("--sweep", action="store_true", help="also time degrees 1..8 and the kernel variants (extra keys)")
     ap.add_argument("--stages", action="store_true", help="the reference's DG (SC) / CG (SC) decomposition and eta (benchmark_01.cc:189-220)")
@@ -238,7 +240,10 @@ def run():
 
     prob = build_problem(mfhn, args, L, rank, world)
     op, mf, n_dofs_global = prob["op"], prob["mf"], prob["n_dofs"]
-    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    if world > 1 and args.exchange == "peer":
+        dst, src = prob["comm"].enable_peer()  # exportable vector pair, peers' vectors mapped through CUDA IPC
+    else:
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
     prob["fill_src"](src)
     t_setup = time.perf_counter() - t_setup
 
@@ -273,13 +278,23 @@ def run():
     value = n_dofs_global / (ms_per_step * 1e-3) / 1e9
     if world > 1:
         # the partitioned operator must keep constants in its null space (exercises both ghost exchanges)
-        ones, chk = op.initialize_dof_vector(), op.initialize_dof_vector()
-        ones.fill_(1.0)
-        op.vmult(chk, ones)
-        worst = chk.abs().max().reshape(1).to(torch.float64)
+        if args.exchange == "peer":  # the check must run on the registered pair to exercise the peer path
+            keep = src.clone()
+            src.fill_(1.0)
+            op.vmult(dst, src, zero_dst=True)
+            worst = dst[:op.n_owned].abs().max().reshape(1).to(torch.float64)
+            src.copy_(keep)
+            dist.barrier()
+            dst.zero_()
+            del keep
+        else:
+            ones, chk = op.initialize_dof_vector(), op.initialize_dof_vector()
+            ones.fill_(1.0)
+            op.vmult(chk, ones)
+            worst = chk.abs().max().reshape(1).to(torch.float64)
+            del ones, chk
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         assert float(worst.item()) < 1e-9, f"distributed vmult failed A*1 = 0: {float(worst.item())}"
-        del ones, chk
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 or L != default_refinements_single(args) else "strong", "vs_baseline": None,
@@ -317,6 +332,7 @@ def run():
                      "n_dofs": int(n_dofs_global), "kernel": prob["kernel_name"], "partition": prob["partition"],
                      "l2": "inputs larger than L2 (vectors + index arrays >> 126 MB), no flush",
                      "dst": "accumulating vmult like benchmark_03.h:352", "setup_s": round(t_setup, 1),
+                     "exchange": args.exchange if world > 1 else None,
                      "launch": "CUDA graph replay of one partitioned vmult" if graph is not None else "host launches"}
 
     if rank == 0 and world == 1 and not args.minimal:

@@ -102,6 +102,13 @@ SIGNATURES = {
     "mfhn_dist_destroy": (None, [c_void_p]),
     "mfhn_dist_vmult": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "mfhn_dist_launch_count": (c_int64, [c_void_p]),
+    "mfhn_vec_alloc": (c_int, [c_int64, P(c_void_p)]),
+    "mfhn_vec_free": (c_int, [c_void_p]),
+    "mfhn_ipc_get_handle": (c_int, [c_void_p, c_void_p]),
+    "mfhn_ipc_open_handle": (c_int, [c_void_p, P(c_void_p)]),
+    "mfhn_ipc_close_handle": (c_int, [c_void_p]),
+    "mfhn_dist_enable_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mfhn_dist_vmult_peer": (c_int, [c_void_p, c_void_p, c_int]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

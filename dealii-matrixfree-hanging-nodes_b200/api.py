@@ -134,7 +134,9 @@ class Partitioner:
         self.n_owned = self.end - self.begin
         self.ghost_global = ghost_global
         self.n_ghost = len(ghost_global)
+        self.rank_begin = np.asarray(rank_begin, dtype=np.int64)
         owner = np.searchsorted(rank_begin, ghost_global, side="right") - 1
+        self.ghost_owner = owner.astype(np.int32)
         # ghosts are sorted by global index, owners' ranges are ascending => contiguous per peer
         self.ghost_ranges = {}
         for p in np.unique(owner):

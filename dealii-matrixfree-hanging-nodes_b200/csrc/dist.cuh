@@ -27,12 +27,14 @@ struct NcclApi
   typedef int (*CommDestroy_t)(void *);
   typedef int (*SendRecv_t)(void *, size_t, int, int, void *, cudaStream_t);
   typedef int (*Group_t)();
+  typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
   typedef const char *(*ErrStr_t)(int);
   GetUniqueId_t GetUniqueId = nullptr;
   CommInitRank_t CommInitRank = nullptr;
   CommDestroy_t CommDestroy = nullptr;
   SendRecv_t Send = nullptr, Recv = nullptr;
   Group_t GroupStart = nullptr, GroupEnd = nullptr;
+  AllReduce_t AllReduce = nullptr;
   ErrStr_t GetErrorString = nullptr;
   bool ok = false;
   std::string error;
@@ -59,8 +61,9 @@ struct NcclApi
     a.Recv           = (SendRecv_t)dlsym(h, "ncclRecv");
     a.GroupStart     = (Group_t)dlsym(h, "ncclGroupStart");
     a.GroupEnd       = (Group_t)dlsym(h, "ncclGroupEnd");
+    a.AllReduce      = (AllReduce_t)dlsym(h, "ncclAllReduce");
     a.GetErrorString = (ErrStr_t)dlsym(h, "ncclGetErrorString");
-    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd && a.GetErrorString;
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd && a.GetErrorString && a.AllReduce;
     if (!a.ok) a.error = "libnccl.so.2 lacks a required symbol";
     return a;
   }

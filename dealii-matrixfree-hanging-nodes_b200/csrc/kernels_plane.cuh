@@ -67,6 +67,11 @@ struct PlaneParams
   long long cell_begin, cell_end, batch_begin, batch_end;
   int apply_constraints;
   cudaTextureObject_t src_tex; // src bound as a linear texture: gathers go through the TEX pipe
+  // peer mode (boundary cells of a partitioned operator): ghost entries (index >= n_owned) are read from /
+  // added to the OWNER's vectors through peer-mapped pointers over NVLink instead of a local ghost section
+  long long n_owned;
+  const void *const *ghost_src; // [n_ghost] address of the entry in the owner's src
+  void *const *ghost_dst;       // [n_ghost] address of the entry in the owner's dst
 };
 
 template <typename Number>
@@ -263,7 +268,7 @@ __device__ __forceinline__ void decode_mask_kernel_axes(unsigned m, unsigned &fa
   cb   = rot3(cb);
 }
 
-template <int n, typename Number, bool TEX>
+template <int n, typename Number, bool TEX, bool PEER = false>
 __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 3)) plane_cell_kernel(const PlaneParams p)
 {
   using Cfg = PlaneCfg<n, Number>;
@@ -295,7 +300,12 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
     for (int j = 0; j < n * n; ++j) idx[j] = valid ? __ldg(ip + j * 32) : 0u; // every entry of a valid cell is a valid index
 #pragma unroll
     for (int j = 0; j < n * n; ++j)
-      u[j / n][j % n] = valid ? (TEX ? tex_fetch<Number>(p.src_tex, idx[j]) : __ldg(src + idx[j])) : Number(0);
+      {
+        if (PEER && valid && idx[j] >= (uint32_t)p.n_owned) // remote entry: plain load through the peer mapping
+          u[j / n][j % n] = *static_cast<const Number *>(p.ghost_src[idx[j] - (uint32_t)p.n_owned]);
+        else
+          u[j / n][j % n] = valid ? (TEX ? tex_fetch<Number>(p.src_tex, idx[j]) : __ldg(src + idx[j])) : Number(0);
+      }
   }
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
@@ -374,7 +384,11 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
 #pragma unroll
       for (int j = 0; j < n * n; ++j)
         {
-          atomicAdd(dst + __ldg(ip + j * 32), cellA[t * ps + j]);
+          const uint32_t g = __ldg(ip + j * 32);
+          if (PEER && g >= (uint32_t)p.n_owned) // red over NVLink into the owner's dst
+            atomicAdd(static_cast<Number *>(p.ghost_dst[g - (uint32_t)p.n_owned]), cellA[t * ps + j]);
+          else
+            atomicAdd(dst + g, cellA[t * ps + j]);
         }
     }
 }
@@ -394,8 +408,16 @@ struct PlaneLayout
   void build(int n_, long long n_cells_, const uint32_t *idx);
 };
 
+struct PeerTables
+{
+  long long n_owned           = 0;
+  const void *const *ghost_src = nullptr;
+  void *const *ghost_dst       = nullptr;
+};
+
 template <int n, typename Number>
-void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex)
+void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex,
+                       const PeerTables *peer = nullptr)
 {
   using Cfg = PlaneCfg<n, Number>;
   static bool attr[64] = {};
@@ -419,10 +441,24 @@ void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
   p.src_tex           = tex;
+  p.n_owned           = peer ? peer->n_owned : 0;
+  p.ghost_src         = peer ? peer->ghost_src : nullptr;
+  p.ghost_dst         = peer ? peer->ghost_dst : nullptr;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + Cfg::warps - 1) / Cfg::warps);
-  if (tex)
+  if (peer)
+    {
+      static bool pattr[64] = {};
+      if (!pattr[device])
+        {
+          cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
+          if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+          pattr[device] = true;
+        }
+      plane_cell_kernel<n, Number, false, true><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+    }
+  else if (tex)
     plane_cell_kernel<n, Number, true><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
   else
     plane_cell_kernel<n, Number, false><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
@@ -431,10 +467,11 @@ void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int devic
 }
 
 template <int n, typename Number>
-void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex)
+void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex,
+                  const PeerTables *peer = nullptr)
 {
   if constexpr (plane_supported(n))
-    launch_plane_impl<n, Number>(L, cp, device, stream, tex);
+    launch_plane_impl<n, Number>(L, cp, device, stream, tex, peer);
   else
     throw std::runtime_error("plane kernel not available for this degree");
 }

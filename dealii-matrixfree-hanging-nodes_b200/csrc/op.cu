@@ -644,9 +644,16 @@ struct Dist
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev[4]        = {nullptr, nullptr, nullptr, nullptr};
   long long launches       = 0;
+  // peer mode: registered vector pair + per-ghost addresses inside the owners' vectors
+  void *peer_src_local = nullptr, *peer_dst_local = nullptr;
+  void **d_ghost_src = nullptr, **d_ghost_dst = nullptr;
+  int *d_barrier = nullptr;
 
   ~Dist()
   {
+    cudaFree(d_ghost_src);
+    cudaFree(d_ghost_dst);
+    cudaFree(d_barrier);
     if (comm) NcclApi::get().CommDestroy(comm);
     cudaFree(d_import_idx);
     cudaFree(d_send);
@@ -723,6 +730,49 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
       ++d.launches;
     }
   if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(dstb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
+}
+
+// Peer-memory variant: no pack / unpack and no data-path collective.  Interior cells run first
+// (they touch local entries only); after a barrier the boundary cells read the owners' src
+// entries and add into the owners' dst entries directly over NVLink; a second barrier makes
+// the remote contributions visible before anyone consumes dst.  The barriers are 4-byte NCCL
+// all-reduces on the compute stream.
+template <typename Number>
+void dist_vmult_peer_n(Dist &d, cudaStream_t main)
+{
+  Operator &op = *d.op;
+  CellLoopParams p;
+  p.idx               = op.d_idx;
+  p.masks             = op.d_masks;
+  p.geom              = op.d_geom;
+  p.src               = d.peer_src_local;
+  p.dst               = d.peer_dst_local;
+  p.apply_constraints = op.apply_constraints;
+  PeerTables pt;
+  pt.n_owned   = op.n_owned;
+  pt.ghost_src = d.d_ghost_src;
+  pt.ghost_dst = d.d_ghost_dst;
+  NcclApi &nccl = NcclApi::get();
+  auto launch = [&](long long cb, long long ce, const PeerTables *peer) {
+    if (ce <= cb) return;
+    p.cell_begin = cb;
+    p.cell_end   = ce;
+    switch (op.degree)
+      {
+        case 1: launch_plane<2, Number>(op.plane, p, op.device, main, 0, peer); break;
+        case 2: launch_plane<3, Number>(op.plane, p, op.device, main, 0, peer); break;
+        case 3: launch_plane<4, Number>(op.plane, p, op.device, main, 0, peer); break;
+        case 4: launch_plane<5, Number>(op.plane, p, op.device, main, 0, peer); break;
+        case 5: launch_plane<6, Number>(op.plane, p, op.device, main, 0, peer); break;
+        default: throw NotImplemented("peer mode covers the register-tiled plane kernel (degree <= 5)");
+      }
+    ++op.launches;
+    ++d.launches;
+  };
+  launch(d.seg[0], d.seg[2], nullptr); // interior cells (both partitions): local entries only
+  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2 /*ncclInt32*/, 0 /*ncclSum*/, d.comm, main));
+  launch(d.seg[2], d.seg[3], &pt);     // boundary cells: remote entries over NVLink
+  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2, 0, d.comm, main));
 }
 } // namespace mfhn
 
@@ -999,4 +1049,87 @@ int mfhn_dist_vmult(mfhn_dist h, void *dst, const void *src, void *stream, int z
   });
 }
 int64_t mfhn_dist_launch_count(mfhn_dist h) { return h ? reinterpret_cast<Dist *>(h)->launches : 0; }
+
+int mfhn_vec_alloc(int64_t bytes, void **ptr)
+{
+  return guard([&] {
+    if (!ptr || bytes < 0) throw InvalidArgument("bad argument");
+    CUDA_CHECK(cudaMalloc(ptr, std::max<size_t>((size_t)bytes, 8)));
+    CUDA_CHECK(cudaMemset(*ptr, 0, std::max<size_t>((size_t)bytes, 8)));
+  });
+}
+int mfhn_vec_free(void *ptr)
+{
+  return guard([&] { CUDA_CHECK(cudaFree(ptr)); });
+}
+int mfhn_ipc_get_handle(void *ptr, void *handle64)
+{
+  return guard([&] {
+    if (!ptr || !handle64) throw InvalidArgument("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CUDA_CHECK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle64), ptr));
+  });
+}
+int mfhn_ipc_open_handle(const void *handle64, void **ptr)
+{
+  return guard([&] {
+    if (!ptr || !handle64) throw InvalidArgument("null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+int mfhn_ipc_close_handle(void *ptr)
+{
+  return guard([&] { CUDA_CHECK(cudaIpcCloseMemHandle(ptr)); });
+}
+int mfhn_dist_enable_peer(mfhn_dist h, void *src_local, void *dst_local, void *const *peer_src, void *const *peer_dst,
+                          const int32_t *ghost_owner, const int64_t *ghost_remote_index)
+{
+  return guard([&] {
+    if (!h || !src_local || !dst_local || !peer_src || !peer_dst) throw InvalidArgument("null argument");
+    Dist &d      = *reinterpret_cast<Dist *>(h);
+    Operator &op = *d.op;
+    if (!plane_supported(op.degree + 1) || op.geometry_type != MFHN_GEOM_CARTESIAN)
+      throw NotImplemented("peer mode covers the register-tiled plane kernel (Cartesian cells, degree <= 5)");
+    CUDA_CHECK(cudaSetDevice(op.device));
+    const size_t s = op.number == MFHN_F64 ? 8 : 4;
+    std::vector<void *> gs((size_t)std::max<long long>(op.n_ghost, 1)), gd(gs.size());
+    for (long long g = 0; g < op.n_ghost; ++g)
+      {
+        if (!ghost_owner || !ghost_remote_index) throw InvalidArgument("null argument");
+        const int o = ghost_owner[g];
+        if (o < 0 || o >= d.world || o == d.rank || !peer_src[o] || !peer_dst[o]) throw InvalidArgument("bad ghost owner");
+        gs[g] = static_cast<char *>(peer_src[o]) + (size_t)ghost_remote_index[g] * s;
+        gd[g] = static_cast<char *>(peer_dst[o]) + (size_t)ghost_remote_index[g] * s;
+      }
+    cudaFree(d.d_ghost_src);
+    cudaFree(d.d_ghost_dst);
+    d.d_ghost_src = to_device(gs);
+    d.d_ghost_dst = to_device(gd);
+    if (!d.d_barrier)
+      {
+        CUDA_CHECK(cudaMalloc(&d.d_barrier, sizeof(int)));
+        CUDA_CHECK(cudaMemset(d.d_barrier, 0, sizeof(int)));
+      }
+    d.peer_src_local = src_local;
+    d.peer_dst_local = dst_local;
+  });
+}
+int mfhn_dist_vmult_peer(mfhn_dist h, void *stream, int zero_dst)
+{
+  return guard([&] {
+    if (!h) throw InvalidArgument("null argument");
+    Dist &d = *reinterpret_cast<Dist *>(h);
+    if (!d.peer_src_local) throw InvalidArgument("mfhn_dist_enable_peer has not been called");
+    Operator &op = *d.op;
+    CUDA_CHECK(cudaSetDevice(op.device));
+    cudaStream_t main = static_cast<cudaStream_t>(stream);
+    if (zero_dst) CUDA_CHECK(cudaMemsetAsync(d.peer_dst_local, 0, (size_t)(op.n_owned + op.n_ghost) * (op.number == MFHN_F64 ? 8 : 4), main));
+    if (op.number == MFHN_F64)
+      dist_vmult_peer_n<double>(d, main);
+    else
+      dist_vmult_peer_n<float>(d, main);
+  });
+}
 }

@@ -22,6 +22,40 @@ from . import _capi as capi
 from ._capi import check, lib
 
 
+class DeviceVector:
+    """Device vector allocated by the library (cudaMalloc) so that it can be exported to the other
+    ranks with CUDA IPC; exposes __cuda_array_interface__, `tensor` is a torch view of it."""
+
+    def __init__(self, n, dtype, device):
+        import ctypes as C
+
+        import torch
+
+        self.n, self.itemsize = int(n), torch.empty(0, dtype=dtype).element_size()
+        self.typestr = "<f8" if self.itemsize == 8 else "<f4"
+        p = C.c_void_p()
+        check(lib.mfhn_vec_alloc(self.n * self.itemsize, C.byref(p)))
+        self.ptr = p.value
+        self.tensor = torch.as_tensor(self, device=device)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n,), "typestr": self.typestr, "data": (self.ptr, False), "version": 2, "strides": None}
+
+    def ipc_handle(self):
+        import torch
+
+        h = torch.zeros(64, dtype=torch.uint8)
+        check(lib.mfhn_ipc_get_handle(self.ptr, h.data_ptr()))
+        return h
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.tensor = None
+            lib.mfhn_vec_free(self.ptr)
+            self.ptr = None
+
+
 class GhostExchange:
     """Owns the send/receive buffers and index lists of one rank.
 
@@ -94,9 +128,50 @@ class GhostExchange:
         self._native = h
 
     def __del__(self):
+        for p in getattr(self, "_peer_opened", []):
+            lib.mfhn_ipc_close_handle(p)
+        self._peer_opened = []
         if getattr(self, "_native", None):
             lib.mfhn_dist_destroy(self._native)
             self._native = None
+
+    # -- peer-memory mode: boundary cells access the owners' vectors over NVLink ---------------------
+    def enable_peer(self):
+        """Allocates an exportable (src, dst) vector pair, exchanges the CUDA IPC handles and registers
+        the peers' vectors with the native operator.  vmult on exactly this pair then runs without
+        pack / unpack and without a data-path collective (mfhn_dist_vmult_peer)."""
+        import ctypes as C
+
+        torch, dist, part = self.torch, self.dist, self.part
+        if self._native is None:
+            raise capi.MfhnError(1, "peer mode needs the native (NCCL) operator")
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        n = self.n_owned + self.n_ghost
+        self._peer_src_vec = DeviceVector(n, self.dtype, self.device)
+        self._peer_dst_vec = DeviceVector(n, self.dtype, self.device)
+        mine = torch.cat([self._peer_src_vec.ipc_handle(), self._peer_dst_vec.ipc_handle()]).to(self.device)
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=self.group)
+        psrc = (C.c_void_p * world)()
+        pdst = (C.c_void_p * world)()
+        self._peer_opened = []
+        needed = set(int(o) for o in np.unique(part.ghost_owner)) if part.n_ghost else set()
+        for r in range(world):
+            if r == rank or r not in needed:
+                continue
+            hcpu = allh[r].cpu().contiguous()
+            a, b = C.c_void_p(), C.c_void_p()
+            check(lib.mfhn_ipc_open_handle(hcpu[:64].contiguous().data_ptr(), C.byref(a)))
+            check(lib.mfhn_ipc_open_handle(hcpu[64:].contiguous().data_ptr(), C.byref(b)))
+            psrc[r], pdst[r] = a.value, b.value
+            self._peer_opened += [a.value, b.value]
+        owner = np.ascontiguousarray(part.ghost_owner, dtype=np.int32)
+        remote = np.ascontiguousarray(part.ghost_global - part.rank_begin[part.ghost_owner], dtype=np.int64) if part.n_ghost else np.zeros(0, np.int64)
+        check(lib.mfhn_dist_enable_peer(self._native, self._peer_src_vec.ptr, self._peer_dst_vec.ptr, psrc, pdst,
+                                        owner.ctypes.data_as(C.c_void_p), remote.ctypes.data_as(C.c_void_p)))
+        dist.barrier(group=self.group)  # every rank has opened what it needs before anyone proceeds
+        self.peer_src, self.peer_dst = self._peer_src_vec.tensor, self._peer_dst_vec.tensor
+        return self.peer_dst, self.peer_src
 
     # -- building blocks ---------------------------------------------------------
     def _global_rank(self, p):
@@ -162,7 +237,10 @@ class GhostExchange:
             return
         if self._native is not None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            check(lib.mfhn_dist_vmult(self._native, dst.data_ptr(), src.data_ptr(), stream, 0))
+            if getattr(self, "peer_src", None) is not None and src.data_ptr() == self.peer_src.data_ptr() and dst.data_ptr() == self.peer_dst.data_ptr():
+                check(lib.mfhn_dist_vmult_peer(self._native, stream, 0))  # the registered pair: peer-memory path
+            else:
+                check(lib.mfhn_dist_vmult(self._native, dst.data_ptr(), src.data_ptr(), stream, 0))
             return
         main = torch.cuda.current_stream(self.device)
         comm = self.comm_stream

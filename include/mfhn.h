@@ -222,6 +222,22 @@ void mfhn_dist_destroy(mfhn_dist d);
 int mfhn_dist_vmult(mfhn_dist d, void *dst, const void *src, void *cuda_stream, int zero_dst);
 int64_t mfhn_dist_launch_count(mfhn_dist d);
 
+/* Peer-memory variant of the partitioned vmult (fused compute + exchange): the boundary cells read
+ * the ghost entries from the OWNER's src and add their contributions into the OWNER's dst through
+ * peer-mapped (CUDA IPC) pointers over NVLink -- no pack / unpack kernels, no data-path collective;
+ * two 4-byte all-reduces act as barriers.  The vector pair must come from mfhn_vec_alloc so that it
+ * can be exported; every rank passes the opened peer pointers of all ranks.  Register-tiled plane
+ * kernel only (Cartesian cells, degree <= 5). */
+int mfhn_vec_alloc(int64_t bytes, void **dev_ptr);
+int mfhn_vec_free(void *dev_ptr);
+int mfhn_ipc_get_handle(void *dev_ptr, void *handle64);
+int mfhn_ipc_open_handle(const void *handle64, void **dev_ptr);
+int mfhn_ipc_close_handle(void *dev_ptr);
+int mfhn_dist_enable_peer(mfhn_dist d, void *src_local, void *dst_local, void *const *peer_src,
+                          void *const *peer_dst, const int32_t *ghost_owner,
+                          const int64_t *ghost_remote_index);
+int mfhn_dist_vmult_peer(mfhn_dist d, void *cuda_stream, int zero_dst);
+
 /* Microbenchmarks used for the roofline denominators (bench.py). */
 int mfhn_bench_dfma(int number, int iters, double *tflops);
 
