@@ -732,11 +732,10 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(dstb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
 }
 
-// Peer-memory variant: no pack / unpack and no data-path collective.  Interior cells run first
-// (they touch local entries only); after a barrier the boundary cells read the owners' src
-// entries and add into the owners' dst entries directly over NVLink; a second barrier makes
-// the remote contributions visible before anyone consumes dst.  The barriers are 4-byte NCCL
-// all-reduces on the compute stream.
+// Peer-memory variant: no pack / unpack and no data-path collective.  After a barrier the
+// boundary cells read the owners' src entries and add into the owners' dst entries directly
+// over NVLink; a second barrier makes the remote contributions visible before anyone consumes
+// dst.  The barriers are 4-byte NCCL all-reduces.
 template <typename Number>
 void dist_vmult_peer_n(Dist &d, cudaStream_t main)
 {
@@ -753,26 +752,33 @@ void dist_vmult_peer_n(Dist &d, cudaStream_t main)
   pt.ghost_src = d.d_ghost_src;
   pt.ghost_dst = d.d_ghost_dst;
   NcclApi &nccl = NcclApi::get();
-  auto launch = [&](long long cb, long long ce, const PeerTables *peer) {
+  auto launch = [&](long long cb, long long ce, const PeerTables *peer, cudaStream_t st) {
     if (ce <= cb) return;
     p.cell_begin = cb;
     p.cell_end   = ce;
     switch (op.degree)
       {
-        case 1: launch_plane<2, Number>(op.plane, p, op.device, main, 0, peer); break;
-        case 2: launch_plane<3, Number>(op.plane, p, op.device, main, 0, peer); break;
-        case 3: launch_plane<4, Number>(op.plane, p, op.device, main, 0, peer); break;
-        case 4: launch_plane<5, Number>(op.plane, p, op.device, main, 0, peer); break;
-        case 5: launch_plane<6, Number>(op.plane, p, op.device, main, 0, peer); break;
+        case 1: launch_plane<2, Number>(op.plane, p, op.device, st, 0, peer); break;
+        case 2: launch_plane<3, Number>(op.plane, p, op.device, st, 0, peer); break;
+        case 3: launch_plane<4, Number>(op.plane, p, op.device, st, 0, peer); break;
+        case 4: launch_plane<5, Number>(op.plane, p, op.device, st, 0, peer); break;
+        case 5: launch_plane<6, Number>(op.plane, p, op.device, st, 0, peer); break;
         default: throw NotImplemented("peer mode covers the register-tiled plane kernel (degree <= 5)");
       }
     ++op.launches;
     ++d.launches;
   };
-  launch(d.seg[0], d.seg[2], nullptr); // interior cells (both partitions): local entries only
-  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2 /*ncclInt32*/, 0 /*ncclSum*/, d.comm, main));
-  launch(d.seg[2], d.seg[3], &pt);     // boundary cells: remote entries over NVLink
-  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2, 0, d.comm, main));
+  // high-priority stream: barrier (peers' src final, peers' dst zeroed) -> boundary cells with remote
+  // entries over NVLink -> barrier (remote contributions landed); the interior cells (local entries
+  // only) run concurrently on the compute stream and hide the whole chain
+  CUDA_CHECK(cudaEventRecord(d.ev[0], main));
+  CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[0], 0));
+  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2 /*ncclInt32*/, 0 /*ncclSum*/, d.comm, d.comm_stream));
+  launch(d.seg[2], d.seg[3], &pt, d.comm_stream);
+  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2, 0, d.comm, d.comm_stream));
+  CUDA_CHECK(cudaEventRecord(d.ev[3], d.comm_stream));
+  launch(d.seg[0], d.seg[2], nullptr, main);
+  CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
 }
 } // namespace mfhn
 
