@@ -570,6 +570,7 @@ __global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n
   // FEEvaluationHangingNodesFactory::apply on cell-local values (benchmark_00_likwid.cc:56-59)
   __shared__ Number s[n * n * n];
   const long long cell = blockIdx.x;
+  if (masks[cell] == 0) return; // unconstrained cell: nothing to interpolate (block-uniform)
   const int l = threadIdx.x, a = l % n, b = l / n;
   Number *g = values + cell * (n * n * n);
   for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
