@@ -268,9 +268,13 @@ class LaplaceOperator:
                 raise capi.MfhnError(1, f"{name} must be a C-contiguous {np.dtype(dtype).name} array of shape {shape}")
         if geometry is None:
             gtype, geom = capi.GEOM_CARTESIAN, matrix_free.h
-        else:  # (n_cells, 3, 3) Jacobians
+        elif np.ndim(geometry) == 3 and np.shape(geometry)[1:] == (3, 3):  # (n_cells, 3, 3) Jacobians
             gtype, geom = capi.GEOM_AFFINE, np.ascontiguousarray(geometry, dtype=np.float64).reshape(-1, 9)
             assert geom.shape[0] == matrix_free.n_cells
+        else:  # (n_cells, 6, (k+1)^3): JxW J^-1 J^-T per quadrature point
+            gtype, geom = capi.GEOM_GENERAL, np.ascontiguousarray(geometry, dtype=np.float64)
+            if geom.shape != (matrix_free.n_cells, 6, n3):
+                raise capi.MfhnError(1, f"general geometry must have shape {(matrix_free.n_cells, 6, n3)}")
         desc = capi.OpDesc(
             degree=matrix_free.degree, number=self.number, n_cells=matrix_free.n_cells, n_owned=part.n_owned,
             n_ghost=part.n_ghost, dof_indices=_ptr(matrix_free.dof_indices), masks=_ptr(matrix_free.masks),

@@ -30,7 +30,9 @@ enum GenericVariant
 {
   GV_QPOINT_CARTESIAN = 0, // collocation gradients, diagonal q-point factor w_q h
   GV_QPOINT_METRIC    = 1, // collocation gradients, symmetric 3x3 metric per cell
-  GV_SEPARABLE        = 2  // h (K x M x M + M x K x M + M x M x K)
+  GV_SEPARABLE        = 2, // h (K x M x M + M x K x M + M x M x K)
+  GV_QPOINT_GENERAL   = 3  // collocation gradients, symmetric 3x3 coefficient per QUADRATURE POINT
+                           // (JxW J^-1 J^-T, [cell][6][q]): curved cells / high-order mappings
 };
 
 template <int n, int T, bool transpose, typename Number>
@@ -103,7 +105,7 @@ struct GenericCfg
 template <int VARIANT>
 __host__ __device__ constexpr int generic_n_arrays()
 {
-  return VARIANT == GV_QPOINT_METRIC ? 4 : 2;
+  return (VARIANT == GV_QPOINT_METRIC || VARIANT == GV_QPOINT_GENERAL) ? 4 : 2;
 }
 
 // DIAG = true computes the diagonal of the operator instead of applying it: for every local
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
           if (valid)
             {
 #pragma unroll
-              for (int i = 0; i < 6; ++i) G[i] = static_cast<const Number *>(p.geom)[cell * 6 + i];
+              for (int i = 0; i < 6; ++i)
+                if (VARIANT == GV_QPOINT_METRIC) G[i] = static_cast<const Number *>(p.geom)[cell * 6 + i];
             }
           load_line<n>(A0 + bx, sx, u);
           mat_vec<n, T_DC, false>(u, v);
@@ -300,7 +303,18 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
             for (int z = 0; z < n; ++z)
               {
                 const Number gx = GX[bz + z * sz], gy = GY[bz + z * sz], gz = GZ[bz + z * sz];
-                const Number ww = wA * wB * wq[z];
+                Number ww = wA * wB * wq[z];
+                if (VARIANT == GV_QPOINT_GENERAL)
+                  {
+                    // submit_gradient with this point's own coefficient (JxW included): coalesced over (x,y)
+                    ww = Number(1);
+                    if (valid)
+                      {
+                        const Number *gq = static_cast<const Number *>(p.geom) + (cell * 6) * (long long)(n * n * n) + (l + n * n * z);
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) G[i] = __ldg(gq + i * (n * n * n));
+                      }
+                  }
                 GX[bz + z * sz] = ww * (G[0] * gx + G[1] * gy + G[2] * gz);
                 GY[bz + z * sz] = ww * (G[1] * gx + G[3] * gy + G[4] * gz);
                 GZ[bz + z * sz] = ww * (G[2] * gx + G[4] * gy + G[5] * gz);

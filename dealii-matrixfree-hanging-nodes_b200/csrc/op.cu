@@ -329,6 +329,8 @@ void launch_diagonal_n(Operator &op, const CellLoopParams &p, cudaStream_t strea
 {
   if (op.geometry_type == MFHN_GEOM_AFFINE)
     launch_generic<n, Number, GV_QPOINT_METRIC, true>(op, p, stream);
+  else if (op.geometry_type == MFHN_GEOM_GENERAL)
+    launch_generic<n, Number, GV_QPOINT_GENERAL, true>(op, p, stream);
   else
     launch_generic<n, Number, GV_SEPARABLE, true>(op, p, stream);
   ++op.launches;
@@ -401,6 +403,8 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
     launch_plane_smem<n, Number>(op.plane, p, op.device, stream);
   else if (op.geometry_type == MFHN_GEOM_AFFINE)
     launch_generic<n, Number, GV_QPOINT_METRIC>(op, p, stream);
+  else if (op.geometry_type == MFHN_GEOM_GENERAL)
+    launch_generic<n, Number, GV_QPOINT_GENERAL>(op, p, stream);
   else if (kernel == MFHN_KERNEL_SEPARABLE)
     launch_generic<n, Number, GV_SEPARABLE>(op, p, stream);
   else
@@ -430,8 +434,8 @@ int resolve_kernel(const Operator &op)
   int kernel = op.kernel;
   if (kernel == MFHN_KERNEL_AUTO)
     kernel = op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_PLANE : MFHN_KERNEL_QPOINT;
-  if (op.geometry_type == MFHN_GEOM_AFFINE && kernel != MFHN_KERNEL_QPOINT)
-    throw InvalidArgument("affine geometry requires MFHN_KERNEL_QPOINT");
+  if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT)
+    throw InvalidArgument("affine / general geometry requires MFHN_KERNEL_QPOINT");
   if (kernel == MFHN_KERNEL_PATCH && !plane_supported(op.degree + 1))
     throw NotImplemented("MFHN_KERNEL_PATCH is not available for this degree");
   if (kernel == MFHN_KERNEL_PATCH && op.patch.d_uidx == nullptr)
@@ -469,7 +473,8 @@ Operator *op_create(const mfhn_op_desc &d)
   if (d.number != MFHN_F64 && d.number != MFHN_F32) throw InvalidArgument("number must be MFHN_F64 or MFHN_F32");
   if (d.n_cells < 0 || d.n_owned < 0 || d.n_ghost < 0) throw InvalidArgument("negative size");
   if (d.n_cells > 0 && (!d.dof_indices || !d.masks || !d.geometry)) throw InvalidArgument("null array");
-  if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE) throw InvalidArgument("unknown geometry type");
+  if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE && d.geometry_type != MFHN_GEOM_GENERAL)
+    throw InvalidArgument("unknown geometry type");
   if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_PATCH) throw InvalidArgument("unknown kernel");
   int device = d.device;
   if (device < 0)
@@ -507,6 +512,8 @@ Operator *op_create(const mfhn_op_desc &d)
   std::vector<double> g;
   if (d.geometry_type == MFHN_GEOM_CARTESIAN)
     g.assign(d.geometry, d.geometry + d.n_cells);
+  else if (d.geometry_type == MFHN_GEOM_GENERAL)
+    g.assign(d.geometry, d.geometry + d.n_cells * 6 * n3); // [cell][6][q], JxW J^-1 J^-T per quadrature point
   else
     {
       g.resize(d.n_cells * 6);
@@ -915,9 +922,9 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
     else if (w == "n_cells_hn")
       *value = (double)op.n_cells_hn;
     else if (w == "algorithmic_bytes") // 2 s n_dofs + n_cells (4 (k+1)^3 + 1 + G)
-      *value = 2 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : 10 * s));
+      *value = 2 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : op.geometry_type == MFHN_GEOM_AFFINE ? 10 * s : 6 * s * n3));
     else if (w == "algorithmic_bytes_accumulate") // + s n_dofs: dst is read as well when vmult accumulates
-      *value = 3 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : 10 * s));
+      *value = 3 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : op.geometry_type == MFHN_GEOM_AFFINE ? 10 * s : 6 * s * n3));
     else if (w == "algorithmic_flops") // even-odd sum factorisation count of SURVEY 8d, without HN terms
       *value = (double)op.n_cells * (12 * n * n * (n * n + 2 * n) + 3 * n3);
     else if (w == "unique_dofs_per_cell")

@@ -41,6 +41,9 @@ typedef struct mfhn_op_s *mfhn_op;
 /* geometry descriptions accepted by mfhn_op_create */
 #define MFHN_GEOM_CARTESIAN 0 /* one double per cell: edge length h                       */
 #define MFHN_GEOM_AFFINE 1    /* nine doubles per cell: Jacobian J[r][c] = dx_r/dxi_c      */
+#define MFHN_GEOM_GENERAL 2   /* [cell][6][(k+1)^3] doubles: symmetric JxW J^-1 J^-T (xx,xy,xz,yy,yz,zz)
+                                 per quadrature point, lexicographic -- curved cells / high-order
+                                 mappings (TestHighOrderMapping, benchmark_01.h:225-242)   */
 
 /* cell kernels */
 #define MFHN_KERNEL_AUTO 0

@@ -94,6 +94,49 @@ def cell_laplace(u, h, degree):
     return r
 
 
+def cell_laplace_general(u, G, degree):
+    """The same evaluate / q-point / integrate sequence with a symmetric 3x3 coefficient per quadrature
+    point, G[c, (xx,xy,xz,yy,yz,zz), q] = JxW J^-1 J^-T (lexicographic q): curved cells / high-order mappings
+    (TestHighOrderMapping, benchmark_01.h:225-242)."""
+    sd = fe1d.shape_data(degree)
+    S, Dc = sd.S, sd.Dc
+    n = degree + 1
+    uq = np.einsum("qx,czyx->czyq", S, u)
+    uq = np.einsum("qy,czyx->czqx", S, uq)
+    uq = np.einsum("qz,czyx->cqyx", S, uq)
+    gx = np.einsum("qx,czyx->czyq", Dc, uq)
+    gy = np.einsum("qy,czyx->czqx", Dc, uq)
+    gz = np.einsum("qz,czyx->cqyx", Dc, uq)
+    Gq = G.reshape(-1, 6, n, n, n)
+    hx = Gq[:, 0] * gx + Gq[:, 1] * gy + Gq[:, 2] * gz
+    hy = Gq[:, 1] * gx + Gq[:, 3] * gy + Gq[:, 4] * gz
+    hz = Gq[:, 2] * gx + Gq[:, 4] * gy + Gq[:, 5] * gz
+    r = np.einsum("qx,czyq->czyx", Dc, hx)
+    r += np.einsum("qy,czqx->czyx", Dc, hy)
+    r += np.einsum("qz,cqyx->czyx", Dc, hz)
+    r = np.einsum("qz,cqyx->czyx", S, r)
+    r = np.einsum("qy,czqx->czyx", S, r)
+    r = np.einsum("qx,czyq->czyx", S, r)
+    return r
+
+
+def vmult_general(lay, src, G, apply_constraints=True, chunk=2048):
+    """dst = A src with per-quadrature-point coefficients (fast hanging-node algorithm around it)."""
+    n = lay.degree + 1
+    dst = np.zeros_like(src)
+    for c0 in range(0, lay.n_cells, chunk):
+        c1 = min(lay.n_cells, c0 + chunk)
+        idx = lay.dof_indices[c0:c1]
+        u = src[idx].reshape(-1, n, n, n)
+        if apply_constraints:
+            hn_apply(u, lay.kinds[c0:c1], lay.degree, transpose=False)
+        r = cell_laplace_general(u, G[c0:c1], lay.degree)
+        if apply_constraints:
+            hn_apply(r, lay.kinds[c0:c1], lay.degree, transpose=True)
+        np.add.at(dst, idx.ravel(), r.ravel())
+    return dst
+
+
 def vmult_abs_bound(lay, src, chunk=4096):
     """|A| |src| evaluated through the same pipeline with every 1D matrix replaced by
     its absolute value: the magnitude any floating-point evaluation of A src works

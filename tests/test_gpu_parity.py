@@ -278,3 +278,71 @@ def test_diagonal_and_jacobi_cg(mfhn, geo, L, k):
     x2 = op.initialize_dof_vector()
     its_plain, _ = mfhn.solve_cg(op, x2, b, diag=None, rel_tol=1e-10, max_iter=4000)
     assert its_jacobi <= its_plain  # the preconditioner pays off on the graded mesh
+
+
+def test_general_per_quadrature_point_geometry(mfhn):
+    """MFHN_GEOM_GENERAL: one symmetric coefficient JxW J^-1 J^-T per quadrature point -- the data class of the
+    reference's TestHighOrderMapping (benchmark_01.h:225-242).  (i) Cartesian coefficients reproduce the Cartesian
+    operator; (ii) the smooth deformation x = X + 1e-2 sin(pi X) matches the numpy restatement; (iii) the operator
+    stays symmetric and keeps the constants in its null space."""
+    import torch
+
+    from oracle import fe1d
+
+    k = 3
+    n = k + 1
+    dh, mf, lay = _case(mfhn, "annulus", 5, "serial", k)
+    # the operator's cells are reordered: build the oracle layout in the same order
+    import copy
+
+    perm = {tuple(c): i for i, c in enumerate(lay.cells.tolist())}
+    cells = mfhn.Triangulation("annulus", 5, "serial").cells()[mf.cell_ids]
+    order = np.array([perm[tuple(c)] for c in cells.tolist()])
+    lo = copy.copy(lay)
+    lo.cells, lo.dof_indices, lo.kinds, lo.masks, lo.h = lay.cells[order], lay.dof_indices[order], lay.kinds[order], lay.masks[order], lay.h[order]
+    assert np.array_equal(lo.dof_indices, mf.dof_indices) and np.array_equal(lo.masks, mf.masks)
+    sd = fe1d.shape_data(k)
+    q, w = sd.qpts, sd.qw
+    w3 = (w[:, None, None] * w[None, :, None] * w[None, None, :]).ravel()  # [z][y][x] -> lexicographic x fastest
+    x = _src(lay, "random")
+
+    def run(G):
+        op = mfhn.LaplaceOperator(mf, kernel="qpoint", geometry=G)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.copy_(torch.from_numpy(x))
+        op.vmult(dst, src)
+        return dst.cpu().numpy(), op
+
+    # (i) Cartesian: JxW J^-1 J^-T = w_q h I
+    G = np.zeros((mf.n_cells, 6, n ** 3))
+    for comp in (0, 3, 5):
+        G[:, comp, :] = lo.h[:, None] * w3[None, :]
+    ref = operators.vmult_fast(lo, x)
+    y, _ = run(G)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12
+    assert np.abs(operators.vmult_general(lo, x, G) - ref).max() / np.abs(ref).max() < 1e-12
+    # (ii) x = X + eps sin(pi X) componentwise: J = h diag(1 + eps pi cos(pi X_d)) at the quadrature points
+    eps = 1e-2
+    hh = lo.h
+    org = -1.0 + lo.cells[:, 1:4] * hh[:, None]
+    qx = np.tile(q, n * n)
+    qy = np.tile(np.repeat(q, n), n)
+    qz = np.repeat(q, n * n)
+    X = [org[:, d, None] + hh[:, None] * qq[None, :] for d, qq in enumerate((qx, qy, qz))]
+    Jd = [hh[:, None] * (1 + eps * np.pi * np.cos(np.pi * X[d])) for d in range(3)]
+    det = Jd[0] * Jd[1] * Jd[2]
+    G = np.zeros((mf.n_cells, 6, n ** 3))
+    for comp, d in ((0, 0), (3, 1), (5, 2)):
+        G[:, comp, :] = w3[None, :] * det / (Jd[d] * Jd[d])
+    ref = operators.vmult_general(lo, x, G)
+    y, op = run(G)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12
+    # (iii) symmetry and null space
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.fill_(1.0)
+    op.vmult(dst, src)
+    assert dst.abs().max().item() < 1e-11
+    b = np.random.default_rng(9).uniform(-1, 1, lay.n_dofs)
+    Ab = operators.vmult_general(lo, b, G)
+    live = ref != 0
+    assert abs(b[live] @ y[live] - x[live] @ Ab[live]) < 1e-10 * abs(b[live] @ y[live])
