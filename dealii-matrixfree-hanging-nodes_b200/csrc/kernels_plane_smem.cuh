@@ -21,7 +21,7 @@ struct PlaneSmemCfg
 {
   using Plane = PlaneCfg<n, Number>;
   static constexpr int cpw = Plane::cpw, ps = Plane::ps, cs = Plane::cs;
-  static constexpr int warps = (2 * cpw * cs * (int)sizeof(Number) > 24 * 1024) ? 2 : 4;
+  static constexpr int warps = (2 * cpw * cs * (int)sizeof(Number) > 20 * 1024) ? 2 : 4; // 2-warp CTAs pack the SM better when a warp needs > 20 KB
   static constexpr int smem  = warps * 2 * cpw * cs * (int)sizeof(Number);
   static constexpr int rows_in_flight = n <= 7 ? 4 : 3; // gather rows issued before the first use
 };
