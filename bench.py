@@ -348,7 +348,7 @@ def run():
         out["eta5"] = max((t_hn / (t_n / n_all) - (n_all - n_hn)) / n_hn, 1.0) if n_hn else 1.0
         # the other kernels on the same problem, for the record
         variants = {}
-        for kname in ("qpoint", "separable", "baseline"):
+        for kname in ("plane", "bulk", "qpoint", "separable", "baseline"):
             try:
                 op.set_kernel(kname)
                 _, pk = time_vmult(torch, op, dst, src, 10, 3)

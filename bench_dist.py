@@ -35,7 +35,7 @@ def build_problem(mfhn, args, L, rank, world):
         i = torch.arange(src.numel(), device=src.device, dtype=torch.float64)
         src.copy_(torch.sin(1e-3 * i).to(src.dtype))
 
-    kname = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch"}[int(op.query("kernel"))]
+    kname = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch", 6: "bulk"}[int(op.query("kernel"))]
     return {"op": op, "mf": mf, "dh": dh, "tria": tria, "n_dofs": dh.n_dofs(), "n_cells_global": tria.n_active_cells(),
             "n_cells_hn_global": tria.n_cells_with_hanging_nodes(), "fill_src": fill_src, "kernel_name": kname,
             "partition": partition, "launches_per_step": launches, "comm": comm}

@@ -268,6 +268,68 @@ __device__ __forceinline__ void decode_mask_kernel_axes(unsigned m, unsigned &fa
   cb   = rot3(cb);
 }
 
+// The seven sweeps of one cell: u = this thread's plane [Y][X] (thread = Z); on return the warp's shared-memory
+// array holds h (K x M x M + M x K x M + M x M x K) u in the layout cellA[Z * ps + Y * n + X] (warp-synchronised).
+template <int n, typename Number>
+__device__ __forceinline__ void plane_sweeps(const Number (&u)[n][n], Number *cellA, const int t, const Number h)
+{
+  using Cfg = PlaneCfg<n, Number>;
+  constexpr int ps = Cfg::ps;
+  // ---- P1: x and y sweeps (thread = Z) ----------------------------------------------
+  // a = M_Y M_X u and b = (M_Y K_X + K_Y M_X) u cross the transpose through the same
+  // shared-memory array one after the other (half the shared memory, more warps per SM)
+  Number az[n][n], bz[n][n]; // P2 operands of this thread: [Y][Z]
+  {
+    Number bb[n][n];
+    {
+      Number pp[n][n], qq[n][n];
+#pragma unroll
+      for (int y = 0; y < n; ++y) apply_MK<n>(u[y], pp[y], qq[y]);
+#pragma unroll
+      for (int x = 0; x < n; ++x)
+        {
+          Number pc[n], qc[n], a[n], b[n];
+#pragma unroll
+          for (int i = 0; i < n; ++i)
+            {
+              pc[i] = pp[i][x];
+              qc[i] = qq[i][x];
+            }
+          apply_M_MK<n>(pc, qc, a, b);
+#pragma unroll
+          for (int i = 0; i < n; ++i)
+            {
+              cellA[t * ps + i * n + x] = a[i];
+              bb[i][x]                  = b[i];
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int y = 0; y < n; ++y)
+#pragma unroll
+      for (int z = 0; z < n; ++z) az[y][z] = cellA[z * ps + y * n + t];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = bb[j / n][j % n];
+    __syncwarp();
+#pragma unroll
+    for (int y = 0; y < n; ++y)
+#pragma unroll
+      for (int z = 0; z < n; ++z) bz[y][z] = cellA[z * ps + y * n + t];
+  }
+  // ---- P2: Z sweep (thread = X) ------------------------------------------------------
+#pragma unroll
+  for (int y = 0; y < n; ++y)
+    {
+      Number r[n];
+      apply_Mb_Ka<n>(az[y], bz[y], r);
+#pragma unroll
+      for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
+    }
+  __syncwarp();
+}
+
 template <int n, typename Number, bool TEX, bool PEER = false>
 __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 3)) plane_cell_kernel(const PlaneParams p)
 {
@@ -324,59 +386,7 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
       __syncwarp();
     }
 
-  // ---- P1: x and y sweeps (thread = Z) ----------------------------------------------
-  // a = M_Y M_X u and b = (M_Y K_X + K_Y M_X) u cross the transpose through the same
-  // shared-memory array one after the other (half the shared memory, more warps per SM)
-  Number az[n][n], bz[n][n]; // P2 operands of this thread: [Y][Z]
-  {
-    Number bb[n][n];
-    {
-      Number pp[n][n], qq[n][n];
-#pragma unroll
-      for (int y = 0; y < n; ++y) apply_MK<n>(u[y], pp[y], qq[y]);
-#pragma unroll
-      for (int x = 0; x < n; ++x)
-        {
-          Number pc[n], qc[n], a[n], b[n];
-#pragma unroll
-          for (int i = 0; i < n; ++i)
-            {
-              pc[i] = pp[i][x];
-              qc[i] = qq[i][x];
-            }
-          apply_M_MK<n>(pc, qc, a, b);
-#pragma unroll
-          for (int i = 0; i < n; ++i)
-            {
-              cellA[t * ps + i * n + x] = a[i];
-              bb[i][x]                  = b[i];
-            }
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int y = 0; y < n; ++y)
-#pragma unroll
-      for (int z = 0; z < n; ++z) az[y][z] = cellA[z * ps + y * n + t];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = bb[j / n][j % n];
-    __syncwarp();
-#pragma unroll
-    for (int y = 0; y < n; ++y)
-#pragma unroll
-      for (int z = 0; z < n; ++z) bz[y][z] = cellA[z * ps + y * n + t];
-  }
-  // ---- P2: Z sweep (thread = X) ------------------------------------------------------
-#pragma unroll
-  for (int y = 0; y < n; ++y)
-    {
-      Number r[n];
-      apply_Mb_Ka<n>(az[y], bz[y], r);
-#pragma unroll
-      for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
-    }
-  __syncwarp();
+  plane_sweeps<n>(u, cellA, t, h);
   if (any_hn) hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t);
   // ---- P3: scatter (thread = z) --------------------------------------------------------
   if (active && valid)

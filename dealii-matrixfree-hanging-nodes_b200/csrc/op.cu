@@ -6,6 +6,7 @@
 #include "fe1d.hpp"
 #include "kernels_generic.cuh"
 #include "kernels_plane.cuh"
+#include "kernels_bulk.cuh"
 #include "kernels_patch.cuh"
 #include "kernels_plane_smem.cuh"
 #include "dist.cuh"
@@ -123,6 +124,47 @@ void PlaneLayout::build(int n_, long long n_cells_, const uint32_t *idx)
         for (int j = 0; j < n2; ++j) p[((size_t)batch * n2 + j) * 32 + slot * n + t] = idx[c * n3 + t + (long long)n * j];
     }
   d_pidx = to_device(p);
+}
+
+// ---- bulk-copy layout -------------------------------------------------------------
+static void bulk_analyze(BulkHostLayout &L, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx)
+{
+  const bool f64 = number == MFHN_F64;
+  switch (n)
+    {
+      case 4: f64 ? bulk_analyze_impl<4, double>(L, n_cells, n_vec, idx) : bulk_analyze_impl<4, float>(L, n_cells, n_vec, idx); break;
+      case 5: f64 ? bulk_analyze_impl<5, double>(L, n_cells, n_vec, idx) : bulk_analyze_impl<5, float>(L, n_cells, n_vec, idx); break;
+      case 6: f64 ? bulk_analyze_impl<6, double>(L, n_cells, n_vec, idx) : bulk_analyze_impl<6, float>(L, n_cells, n_vec, idx); break;
+      default: throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
+    }
+}
+static long long bulk_verify(const BulkHostLayout &L, int number, const uint32_t *idx)
+{
+  const bool f64 = number == MFHN_F64;
+  switch (L.n)
+    {
+      case 4: return f64 ? bulk_verify_impl<4, double>(L, idx) : bulk_verify_impl<4, float>(L, idx);
+      case 5: return f64 ? bulk_verify_impl<5, double>(L, idx) : bulk_verify_impl<5, float>(L, idx);
+      case 6: return f64 ? bulk_verify_impl<6, double>(L, idx) : bulk_verify_impl<6, float>(L, idx);
+      default: throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
+    }
+}
+// more irregular cells than this: the layout does not fit the numbering, the plane kernel runs everything
+constexpr long long bulk_max_irregular = 32;
+
+static void bulk_build(BulkLayout &B, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx)
+{
+  BulkHostLayout L;
+  bulk_analyze(L, n, number, n_cells, n_vec, idx);
+  B.n         = n;
+  B.n_cells   = n_cells;
+  B.n_batches = L.n_batches;
+  B.irregular = L.irregular;
+  B.usable    = (long long)L.irregular.size() <= bulk_max_irregular;
+  if (!B.usable) return;
+  B.d_bidx  = to_device(L.bidx);
+  B.d_lvidx = to_device(L.lvidx);
+  B.d_cinfo = to_device(L.cinfo);
 }
 
 template <int n, typename Number>
@@ -246,6 +288,7 @@ struct Operator
   void *d_geom = nullptr;       // Number h[cell] or Number G[cell][6]
   PlaneLayout plane;            // warp-interleaved layout of the register-tiled kernel
   PatchLayout patch;            // sorted-unique / CSR layout of the patch kernel
+  BulkLayout bulk;              // block descriptors of the bulk-copy kernel (degrees 3..5)
   // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use: 84 B per padded slot)
   uint32_t *d_base_l2g = nullptr;
   void *d_base_invjac = nullptr, *d_base_jxw = nullptr;
@@ -301,6 +344,7 @@ struct Operator
     cudaFree(d_base_jxw);
     plane.free();
     patch.free();
+    bulk.free();
   }
 };
 
@@ -395,7 +439,21 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
       ++op.launches;
       return;
     }
-  if (kernel == MFHN_KERNEL_PATCH)
+  if (kernel == MFHN_KERNEL_BULK)
+    {
+      launch_bulk<n, Number>(op.bulk, p, op.device, stream);
+      // cells that do not show the block pattern: one plane-kernel launch each (at most bulk_max_irregular)
+      for (const long long c : op.bulk.irregular)
+        if (c >= p.cell_begin && c < p.cell_end)
+          {
+            CellLoopParams q = p;
+            q.cell_begin     = c;
+            q.cell_end       = c + 1;
+            launch_plane<n, Number>(op.plane, q, op.device, stream, 0);
+            ++op.launches;
+          }
+    }
+  else if (kernel == MFHN_KERNEL_PATCH)
     launch_patch<n, Number>(op.patch, p, op.device, stream);
   else if (kernel == MFHN_KERNEL_PLANE && plane_supported(n))
     launch_plane<n, Number>(op.plane, p, op.device, stream, op.texture_for(p.src));
@@ -436,11 +494,14 @@ int resolve_kernel(const Operator &op)
     kernel = op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_PLANE : MFHN_KERNEL_QPOINT;
   if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT)
     throw InvalidArgument("affine / general geometry requires MFHN_KERNEL_QPOINT");
+  if (kernel == MFHN_KERNEL_BULK && !bulk_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
+  if (kernel == MFHN_KERNEL_BULK && op.geometry_type == MFHN_GEOM_CARTESIAN && !op.bulk.usable)
+    throw InvalidArgument("MFHN_KERNEL_BULK: the DoF numbering does not show contiguous cell-interior / face blocks");
   if (kernel == MFHN_KERNEL_PATCH && !plane_supported(op.degree + 1))
     throw NotImplemented("MFHN_KERNEL_PATCH is not available for this degree");
   if (kernel == MFHN_KERNEL_PATCH && op.patch.d_uidx == nullptr)
     throw InvalidArgument("the patch layout is built only when the operator is created with MFHN_KERNEL_PATCH");
-  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
+  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
   if (kernel == MFHN_KERNEL_BASELINE && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("the baseline kernel is set up for Cartesian cells");
@@ -461,6 +522,8 @@ void op_vmult_range(Operator &op, void *dst, const void *src, cudaStream_t strea
   p.cell_end          = ce;
   p.apply_constraints = op.apply_constraints;
   const int kernel    = resolve_kernel(op);
+  if (kernel == MFHN_KERNEL_BULK && (((uintptr_t)src | (uintptr_t)dst) & 15u))
+    throw InvalidArgument("MFHN_KERNEL_BULK needs 16-byte aligned vectors (use MFHN_KERNEL_PLANE for unaligned views)");
   if (op.number == MFHN_F64)
     launch_number<double>(op, kernel, p, stream);
   else
@@ -475,7 +538,7 @@ Operator *op_create(const mfhn_op_desc &d)
   if (d.n_cells > 0 && (!d.dof_indices || !d.masks || !d.geometry)) throw InvalidArgument("null array");
   if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE && d.geometry_type != MFHN_GEOM_GENERAL)
     throw InvalidArgument("unknown geometry type");
-  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_PATCH) throw InvalidArgument("unknown kernel");
+  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_BULK) throw InvalidArgument("unknown kernel");
   int device = d.device;
   if (device < 0)
     CUDA_CHECK(cudaGetDevice(&device));
@@ -550,6 +613,7 @@ Operator *op_create(const mfhn_op_desc &d)
           for (int i = 1; i < d.n_segments; ++i)
             if (d.segments[i] < d.segments[i - 1] || d.segments[i] > d.n_cells) throw InvalidArgument("segments must be ascending");
         }
+      if (bulk_supported(n)) bulk_build(op->bulk, n, d.number, d.n_cells, nvec, d.dof_indices);
       if (plane_supported(n) && (d.kernel == MFHN_KERNEL_PATCH || std::getenv("MFHN_BUILD_PATCH"))) op->patch.build(n, d.number, d.n_cells, d.dof_indices);
     }
   resolve_kernel(*op);
@@ -884,7 +948,7 @@ int mfhn_op_set_kernel(mfhn_op h, int kernel)
     if (!h) throw InvalidArgument("null argument");
     Operator &op  = *reinterpret_cast<Operator *>(h);
     const int old = op.kernel;
-    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_PATCH) throw InvalidArgument("unknown kernel");
+    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_BULK) throw InvalidArgument("unknown kernel");
     op.kernel = kernel;
     try
       {
@@ -933,11 +997,26 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
       *value = (double)op.patch.index_bytes;
     else if (w == "kernel")
       *value = (double)resolve_kernel(op);
+    else if (w == "bulk_irregular_cells") // cells the bulk-copy kernel leaves to the plane kernel (-1: layout not usable)
+      *value = op.bulk.usable ? (double)op.bulk.irregular.size() : -1.0;
     else
       throw InvalidArgument("unknown query '" + w + "'");
   });
 }
 int64_t mfhn_op_launch_count(mfhn_op h) { return h ? reinterpret_cast<Operator *>(h)->launches : 0; }
+
+int mfhn_bulk_layout_check(int degree, int number, int64_t n_cells, int64_t n_vec, const uint32_t *dof_indices, int64_t *n_irregular,
+                           int64_t *n_mismatch)
+{
+  return guard([&] {
+    if (n_cells > 0 && !dof_indices) throw InvalidArgument("null argument");
+    if (number != MFHN_F64 && number != MFHN_F32) throw InvalidArgument("number must be MFHN_F64 or MFHN_F32");
+    BulkHostLayout L;
+    bulk_analyze(L, degree + 1, number, n_cells, n_vec, dof_indices);
+    if (n_irregular) *n_irregular = (int64_t)L.irregular.size();
+    if (n_mismatch) *n_mismatch = bulk_verify(L, number, dof_indices);
+  });
+}
 
 int mfhn_pack(int number, void *buffer, const void *vec, const int32_t *idx, int64_t n, void *stream)
 {

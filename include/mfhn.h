@@ -51,7 +51,9 @@ typedef struct mfhn_op_s *mfhn_op;
 #define MFHN_KERNEL_SEPARABLE 2 /* Cartesian cells only: 1D mass/stiffness tensor form        */
 #define MFHN_KERNEL_BASELINE 3  /* restatement of the deal.II CUDA design (one thread per DoF) */
 #define MFHN_KERNEL_PLANE 4     /* Cartesian cells, register-tiled separable kernel, per-cell gather */
-#define MFHN_KERNEL_PATCH 5     /* same arithmetic, patch-wise sorted-unique gather/scatter (fast path) */
+#define MFHN_KERNEL_PATCH 5     /* same arithmetic, patch-wise sorted-unique gather/scatter (experimental) */
+#define MFHN_KERNEL_BULK 6      /* plane kernel; cell-interior and face blocks moved by the bulk-copy engine
+                                   (cp.async.bulk / cp.reduce.async.bulk), degrees 3..5, 16-byte aligned vectors */
 
 const char *mfhn_last_error(void);
 const char *mfhn_version(void);
@@ -240,6 +242,13 @@ int mfhn_dist_enable_peer(mfhn_dist d, void *src_local, void *dst_local, void *c
                           void *const *peer_dst, const int32_t *ghost_owner,
                           const int64_t *ghost_remote_index);
 int mfhn_dist_vmult_peer(mfhn_dist d, void *cuda_stream, int zero_dst);
+
+/* Host-only check of the MFHN_KERNEL_BULK layout for a reference index array (read_dof_values order,
+ * benchmark_03.h:255-258): n_irregular = cells that do not show contiguous cell-interior / face blocks
+ * (they run through the plane kernel), n_mismatch = entries an emulated gather through the layout gets
+ * wrong (must be 0).  Needs no GPU. */
+int mfhn_bulk_layout_check(int degree, int number, int64_t n_cells, int64_t n_vec, const uint32_t *dof_indices,
+                           int64_t *n_irregular, int64_t *n_mismatch);
 
 /* Microbenchmarks used for the roofline denominators (bench.py). */
 int mfhn_bench_dfma(int number, int iters, double *tflops);

@@ -44,7 +44,7 @@ def _run(mfhn, mf, x, number, kernel, apply_constraints=True):
     return dst.cpu().numpy().astype(np.float64), op
 
 
-KERNELS = ["qpoint", "separable", "plane", "patch", "baseline"]
+KERNELS = ["qpoint", "separable", "plane", "bulk", "patch", "baseline"]
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
@@ -53,6 +53,8 @@ KERNELS = ["qpoint", "separable", "plane", "patch", "baseline"]
 def test_vmult_matches_oracle_annulus(mfhn, k, kernel, number):
     if kernel == "patch" and k > 5:
         pytest.skip("the patch kernel covers degree <= 5")
+    if kernel == "bulk" and not 3 <= k <= 5:
+        pytest.skip("the bulk-copy kernel covers degrees 3..5")
     L = 5 if k <= 4 else 4 if k <= 6 else 3
     geo = "annulus" if k <= 4 else "quadrant"
     dh, mf, lay = _case(mfhn, geo, L, "serial", k)
@@ -78,6 +80,36 @@ def test_vmult_without_constraints(mfhn, kernel):
     ref = operators.vmult_fast(lay, x, apply_constraints=False)
     y, _ = _run(mfhn, mf, x, "double", kernel, apply_constraints=False)
     assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_bulk_kernel_ranges_irregular_cells_and_alignment(mfhn, k, number):
+    """MFHN_KERNEL_BULK: cell ranges (the partitions of the overlap schedule), the cells left to the
+    plane kernel (a block that ends at the last vector entry) and the 16-byte alignment rule."""
+    import torch
+
+    dh, mf, lay = _case(mfhn, "quadrant", 3, "p4est", k)
+    x = _src(lay, "random")
+    ref = operators.vmult_fast(lay, x)
+    op = mfhn.LaplaceOperator(mf, number=number, kernel="bulk")
+    assert op.query("bulk_irregular_cells") >= 1  # the hex block of the last cell ends the vector
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.copy_(torch.from_numpy(x).to(src.dtype))
+    cuts = [0, 7, 8, 50, mf.n_cells]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        op.vmult_range(dst, src, b, e)
+    torch.cuda.synchronize()
+    y = dst.cpu().numpy().astype(np.float64)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < TOL[number]
+    # unaligned views are rejected (bulk copies need 16-byte aligned addresses)
+    big = torch.zeros(src.numel() + 4, dtype=src.dtype, device=src.device)
+    with pytest.raises(mfhn.MfhnError):
+        op.vmult(dst, big[1 : 1 + src.numel()])
+    op.set_kernel("plane")
+    dst.zero_()
+    op.vmult(dst, big[1 : 1 + src.numel()])  # the plane kernel takes any view
+    torch.cuda.synchronize()
 
 
 def test_vmult_accumulates_like_reference(mfhn):
