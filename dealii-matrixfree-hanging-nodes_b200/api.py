@@ -188,6 +188,10 @@ class MatrixFree:
         touches = is_ghost.reshape(sub.shape).any(axis=1)
         order = np.concatenate([np.nonzero(~touches)[0], np.nonzero(touches)[0]])
         self.n_interior_cells = int((~touches).sum())
+        if dh.n_ranks > 1:
+            # partition boundaries on whole warp batches of the cell kernels (16, 10, 8, 6, 5, 4 cells per warp for
+            # k = 1..6; lcm 240): the last few interior cells simply join the boundary partition
+            self.n_interior_cells -= self.n_interior_cells % 240
         if categorize:
             # the reference's Categorize option (benchmark_01.h:258-284: cell_vectorization_category =
             # constraint mask): inside windows of the Morton order, cells are grouped by their constraint
@@ -202,7 +206,7 @@ class MatrixFree:
             window = np.where(seg == 0, pos, pos - self.n_interior_cells) // w
             order = order[np.lexsort((pos, key, window, seg))]
         # deal.II's cell_loop overlaps the two ghost exchanges with two interior partitions
-        self.n_interior_a = self.n_interior_cells // 2 if dh.n_ranks > 1 else self.n_interior_cells
+        self.n_interior_a = (self.n_interior_cells // 2) // 240 * 240 if dh.n_ranks > 1 else self.n_interior_cells
         self.cell_ids = cells[order]
         self.dof_indices = np.ascontiguousarray(local[order].astype(np.uint32))
         self.masks = np.ascontiguousarray(masks[order])

@@ -137,7 +137,7 @@ struct BulkParams
   const void *h;
   const void *src;
   void *dst;
-  long long cell_begin, cell_end, batch_begin, batch_end;
+  long long batch_begin, batch_end; // whole warp batches (cpw cells each)
   int apply_constraints;
 };
 
@@ -155,7 +155,7 @@ __device__ __forceinline__ void bulk_copy(const unsigned smem, const Number *gme
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem), "r"(smem), "r"(bytes) : "memory");
 }
 
-// The block descriptors of this lane (one hex block for lanes < cpw, NQ quads), bulk_invalid outside the cell range
+// The block descriptors of this lane (one hex block for lanes < cpw, NQ quads), bulk_invalid = none
 template <int n, typename Number>
 __device__ __forceinline__ void bulk_descriptors(const BulkParams &p, const long long batch, const int lane, uint32_t &hexfirst,
                                                  uint32_t (&qfirst)[BulkCfg<n, Number>::NQ])
@@ -164,17 +164,11 @@ __device__ __forceinline__ void bulk_descriptors(const BulkParams &p, const long
   constexpr int cpw = B::P::cpw;
   const uint32_t *bp = p.bidx + batch * (long long)B::brow;
   hexfirst = lane < cpw ? __ldg(bp + lane) : bulk_invalid;
-  {
-    const long long bc = batch * cpw + lane;
-    if (bc < p.cell_begin || bc >= p.cell_end) hexfirst = bulk_invalid;
-  }
 #pragma unroll
   for (int r = 0; r < B::NQ; ++r)
     {
       const int q = r * 32 + lane;
       qfirst[r]   = q < 6 * cpw ? __ldg(bp + cpw + q) : bulk_invalid;
-      const long long bc = batch * cpw + q / 6;
-      if (bc < p.cell_begin || bc >= p.cell_end) qfirst[r] = bulk_invalid;
     }
 }
 
@@ -214,8 +208,7 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
   const bool active = lane < Cfg::lanes;
   const int ml = active ? lane : lane - 16; // idle lanes mirror lane - 16 (see the plane kernel)
   const int c = ml / n, t = ml - c * n;
-  const long long cell = batch * Cfg::cpw + c;
-  const bool in_range  = cell >= p.cell_begin && cell < p.cell_end;
+  const long long cell = batch * Cfg::cpw + c; // the launcher passes whole batches only: every cell exists
   const Number *__restrict__ src = static_cast<const Number *>(p.src);
   Number *__restrict__ dst = static_cast<Number *>(p.dst);
   const uint32_t *lvp = p.lvidx + batch * (long long)(B::R * 32) + lane;
@@ -226,7 +219,7 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
   bulk_descriptors<n, Number>(p, batch, lane, hexfirst, qfirst);
 #pragma unroll
   for (int r = 0; r < B::R; ++r) g[r] = __ldg(lvp + r * 32);
-  const unsigned info = in_range ? __ldg(p.cinfo + cell) : 0x80000000u;
+  const unsigned info = __ldg(p.cinfo + cell);
   const bool valid    = !(info >> 31);
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
@@ -251,9 +244,6 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
 #pragma unroll
     for (int r = 0; r < B::R; ++r)
       {
-        const int e = r * 32 + lane;
-        const long long lc = batch * Cfg::cpw + e / B::lv;
-        if (lc < p.cell_begin || lc >= p.cell_end) g[r] = bulk_invalid;
         v[r] = g[r] != bulk_invalid ? __ldg(src + g[r]) : Number(0);
       }
 #pragma unroll
@@ -269,8 +259,8 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
   __syncwarp();
   asm volatile("{\n.reg .pred pw;\nBULK_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 pw, [%0], 0;\n@!pw bra BULK_WAIT;\n}" ::"r"(bar) : "memory");
 
-  // thread = x, plane slot j = y + n z.  (Cells outside the range or left to the plane kernel compute on
-  // whatever the staging area holds and never store.)
+  // thread = x, plane slot j = y + n z.  (Cells left to the plane kernel compute on whatever the staging
+  // area holds and never store.)
   Number u[n][n];
   {
     const BulkAddr<n, Number> pos(t, info);
@@ -303,9 +293,10 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
 #pragma unroll
     for (int j = 0; j < n * n; ++j) r[j] = cellA[t * ps + j];
     __syncwarp(); // back to the staging layout
-    if (active && valid)
+    const unsigned info2 = __ldg(p.cinfo + cell); // loaded again instead of living through the sweeps
+    if (active && !(info2 >> 31))
       {
-        const BulkAddr<n, Number> pos(t, info);
+        const BulkAddr<n, Number> pos(t, info2);
         Number *S = A + c * B::Ss;
 #pragma unroll
         for (int j = 0; j < n * n; ++j) S[pos(j % n, j / n)] = r[j];
@@ -345,8 +336,6 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
   for (int r = 0; r < B::R; ++r)
     {
       const int e = r * 32 + lane, ec = e / B::lv;
-      const long long lc = batch * Cfg::cpw + ec;
-      if (lc < p.cell_begin || lc >= p.cell_end) g[r] = bulk_invalid;
       if (g[r] != bulk_invalid) atomicAdd(dst + g[r], A[ec * B::Ss + B::LVoff + (e - ec * B::lv)]);
     }
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the staging area must outlive the bulk reads
@@ -399,10 +388,10 @@ void launch_bulk_impl(const BulkLayout &L, const CellLoopParams &cp, int device,
   p.h                 = cp.geom;
   p.src               = cp.src;
   p.dst               = cp.dst;
-  p.cell_begin        = cp.cell_begin;
-  p.cell_end          = cp.cell_end;
+  if (cp.cell_begin % Cfg::cpw || cp.cell_end % Cfg::cpw || cp.cell_end > L.n_batches * Cfg::cpw)
+    throw std::runtime_error("bulk kernel: cell range must consist of whole warp batches");
   p.batch_begin       = cp.cell_begin / Cfg::cpw;
-  p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
+  p.batch_end         = cp.cell_end / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
@@ -434,7 +423,7 @@ void bulk_analyze_impl(BulkHostLayout &L, long long n_cells, long long n_vec, co
   L.n_batches = (n_cells + Cfg::cpw - 1) / Cfg::cpw;
   L.bidx.assign((size_t)std::max<long long>(L.n_batches, 1) * B::brow, bulk_invalid);
   L.lvidx.assign((size_t)std::max<long long>(L.n_batches, 1) * B::R * 32, bulk_invalid);
-  L.cinfo.assign((size_t)std::max<long long>(n_cells, 1), 0x80000000u);
+  L.cinfo.assign((size_t)std::max<long long>(L.n_batches, 1) * Cfg::cpw, 0x80000000u); // padded to whole batches
   std::vector<unsigned char> irr((size_t)std::max<long long>(n_cells, 1), 0);
 #pragma omp parallel for schedule(static)
   for (long long c = 0; c < n_cells; ++c)

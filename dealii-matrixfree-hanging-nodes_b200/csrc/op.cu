@@ -441,17 +441,35 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
     }
   if (kernel == MFHN_KERNEL_BULK)
     {
-      launch_bulk<n, Number>(op.bulk, p, op.device, stream);
-      // cells that do not show the block pattern: one plane-kernel launch each (at most bulk_max_irregular)
+      // the bulk-copy kernel takes whole warp batches; the (at most cpw - 1) cells at either end of an unaligned
+      // range and the cells that do not show the block pattern (at most bulk_max_irregular) go to the plane kernel
+      constexpr long long cpw = PlaneCfg<n, Number>::cpw;
+      // (the last batch of the mesh may be incomplete: its missing cells are marked in the layout)
+      const long long b0 = (p.cell_begin + cpw - 1) / cpw * cpw;
+      const long long b1 = p.cell_end == op.n_cells ? (op.n_cells + cpw - 1) / cpw * cpw : p.cell_end / cpw * cpw;
+      auto plane_part = [&](const long long cb, const long long ce) {
+        if (ce <= cb) return;
+        CellLoopParams q = p;
+        q.cell_begin     = cb;
+        q.cell_end       = ce;
+        launch_plane<n, Number>(op.plane, q, op.device, stream, 0);
+        ++op.launches;
+      };
+      if (b1 <= b0)
+        {
+          plane_part(p.cell_begin, p.cell_end);
+          return;
+        }
+      plane_part(p.cell_begin, b0);
+      {
+        CellLoopParams q = p;
+        q.cell_begin     = b0;
+        q.cell_end       = b1;
+        launch_bulk<n, Number>(op.bulk, q, op.device, stream);
+      }
+      plane_part(b1, p.cell_end);
       for (const long long c : op.bulk.irregular)
-        if (c >= p.cell_begin && c < p.cell_end)
-          {
-            CellLoopParams q = p;
-            q.cell_begin     = c;
-            q.cell_end       = c + 1;
-            launch_plane<n, Number>(op.plane, q, op.device, stream, 0);
-            ++op.launches;
-          }
+        if (c >= b0 && c < std::min(b1, p.cell_end)) plane_part(c, c + 1);
     }
   else if (kernel == MFHN_KERNEL_PATCH)
     launch_patch<n, Number>(op.patch, p, op.device, stream);
@@ -491,7 +509,12 @@ int resolve_kernel(const Operator &op)
 {
   int kernel = op.kernel;
   if (kernel == MFHN_KERNEL_AUTO)
-    kernel = op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_PLANE : MFHN_KERNEL_QPOINT;
+    {
+      kernel = op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_PLANE : MFHN_KERNEL_QPOINT;
+      // measured on B200 (profiles/): the bulk-copy kernel wins for double at k = 4, 5 (the plane kernel is bound by
+      // the L1 data stage there); for float and k = 3 the plane kernel's gathers are cheap enough
+      if (kernel == MFHN_KERNEL_PLANE && op.number == MFHN_F64 && (op.degree == 4 || op.degree == 5) && op.bulk.usable) kernel = MFHN_KERNEL_BULK;
+    }
   if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT)
     throw InvalidArgument("affine / general geometry requires MFHN_KERNEL_QPOINT");
   if (kernel == MFHN_KERNEL_BULK && !bulk_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
@@ -521,9 +544,13 @@ void op_vmult_range(Operator &op, void *dst, const void *src, cudaStream_t strea
   p.cell_begin        = cb;
   p.cell_end          = ce;
   p.apply_constraints = op.apply_constraints;
-  const int kernel    = resolve_kernel(op);
+  int kernel          = resolve_kernel(op);
   if (kernel == MFHN_KERNEL_BULK && (((uintptr_t)src | (uintptr_t)dst) & 15u))
-    throw InvalidArgument("MFHN_KERNEL_BULK needs 16-byte aligned vectors (use MFHN_KERNEL_PLANE for unaligned views)");
+    {
+      if (op.kernel != MFHN_KERNEL_AUTO)
+        throw InvalidArgument("MFHN_KERNEL_BULK needs 16-byte aligned vectors (use MFHN_KERNEL_PLANE for unaligned views)");
+      kernel = MFHN_KERNEL_PLANE; // AUTO: unaligned views take the plane kernel
+    }
   if (op.number == MFHN_F64)
     launch_number<double>(op, kernel, p, stream);
   else
