@@ -299,7 +299,13 @@ def run():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 or L != default_refinements_single(args) else "strong", "vs_baseline": None,
            "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic"}
-    launches_per_step = prob["launches_per_step"]
+    # kernels per step, counted by the engine itself: cell kernels of one vmult (the bulk-copy kernel adds a
+    # plane-kernel launch for every cell it leaves out), plus pack / unpack in partitioned runs
+    c0 = op.launch_count()
+    op.vmult(dst, src)
+    torch.cuda.synchronize()
+    cell_launches = op.launch_count() - c0
+    launches_per_step = cell_launches if world == 1 else prob["comm"].launches_per_vmult(cell_launches)
     out["gpu_launches"] = int(launches_per_step * args.steps)
 
     # roofline of the dominant kernel (the fused cell kernel): algorithmic bytes / average launch time

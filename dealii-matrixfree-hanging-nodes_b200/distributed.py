@@ -278,9 +278,11 @@ class GhostExchange:
             self.vmult(op, dst, src)
         return graph
 
-    def launches_per_vmult(self):
+    def launches_per_vmult(self, cell_launches=None):
+        """Kernels per vmult: cell kernels (measured by the caller through LaplaceOperator.launch_count, or one
+        per non-empty partition) plus the pack / unpack kernels of the exchange."""
         s0, s1, s2, s3 = self.seg
-        cells = int(s1 > s0) + int(s2 > s1) + int(s3 > s2)
+        cells = int(s1 > s0) + int(s2 > s1) + int(s3 > s2) if cell_launches is None else int(cell_launches)
         if self._native is not None:
             return cells + 2 * int(self.part.n_import_indices() > 0)  # one pack + one unpack kernel
         return cells + 2 * len(self.import_peers)
