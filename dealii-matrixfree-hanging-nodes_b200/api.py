@@ -198,8 +198,9 @@ class MatrixFree:
             # mask, so that fewer warps pay for the interpolation and a warp holds few different
             # constraint kinds (= few different interpolation passes); locality is kept at window scale.
             # Measured on B200 (k=4 / k=5): window 240 by flag 84.3 / 82.0, by kind 86.1 / 89.4,
-            # window 960 by kind 86.9 / 93.0, window 3840 by kind 87.2 / 93.8 GDoF/s.
-            w = int(os.environ.get("MFHN_CATEGORIZE_WINDOW", "960"))
+            # window 960 by kind 86.9 / 93.0, window 3840 by kind 87.2 / 93.8 GDoF/s (plane kernel); bulk-copy
+            # kernel at k=4: 960: 95.1, 3840: 95.7, 15360: 93.5.
+            w = int(os.environ.get("MFHN_CATEGORIZE_WINDOW", "3840"))
             key = masks[order].astype(np.int64) if os.environ.get("MFHN_CATEGORIZE_BY_KIND", "1") == "1" else (masks[order] != 0).astype(np.int64)
             seg = (np.arange(len(order)) >= self.n_interior_cells).astype(np.int64)
             pos = np.arange(len(order))

@@ -77,4 +77,4 @@ def test_matrix_free_host_layout(mfhn):
     # Categorize (benchmark_01.h:258-284): same cells, grouped by constraint mask inside Morton windows
     mfc = mfhn.MatrixFree(dh)
     assert sorted(mfc.cell_ids) == sorted(mf.cell_ids) and mfc.n_cells_hn() == mf.n_cells_hn()
-    assert np.abs(pos[mfc.cell_ids] - np.arange(mf.n_cells)).max() < 960
+    assert np.abs(pos[mfc.cell_ids] - np.arange(mf.n_cells)).max() < 3840  # the window (MFHN_CATEGORIZE_WINDOW)
