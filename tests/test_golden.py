@@ -50,11 +50,13 @@ def test_cpp_setup_reproduces_golden_bit_exact(path, mfhn):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", FIXTURES, ids=os.path.basename)
-@pytest.mark.parametrize("kernel", ["qpoint", "separable", "plane", "patch", "baseline"])
+@pytest.mark.parametrize("kernel", ["auto", "qpoint", "separable", "plane", "bulk", "patch", "baseline"])
 def test_cuda_reproduces_golden(path, kernel, mfhn):
     import torch
 
     g = np.load(path)
+    if kernel == "bulk" and not 3 <= int(g["degree"]) <= 5:
+        pytest.skip("the bulk-copy kernel covers degrees 3..5")
     tria = mfhn.Triangulation(str(g["geometry"]), int(g["n_refinements"]), str(g["flavour"]))
     dh = mfhn.DoFHandler(tria, int(g["degree"]))
     mf = mfhn.MatrixFree(dh)
