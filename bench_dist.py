@@ -55,7 +55,7 @@ def degree_sweep(mfhn, torch, args, time_vmult):
             op = mfhn.LaplaceOperator(mf, number=number)
             src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
             src.fill_(1.0)
-            for kern in ("patch", "plane", "separable", "qpoint"):
+            for kern in ("plane", "separable", "qpoint"):
                 try:
                     op.set_kernel(kern)
                 except mfhn.MfhnError:

@@ -69,17 +69,4 @@ struct NcclApi
   }
 };
 
-template <typename Number>
-__global__ void pack_all_kernel(Number *buf, const Number *vec, const int32_t *idx, long long n)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) buf[i] = vec[idx[i]];
-}
-// several peers may contribute to the same owned entry: atomic
-template <typename Number>
-__global__ void unpack_add_all_kernel(Number *vec, const Number *buf, const int32_t *idx, long long n)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(vec + idx[i], buf[i]);
-}
 } // namespace mfhn

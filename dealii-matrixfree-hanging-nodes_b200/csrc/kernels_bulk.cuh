@@ -24,9 +24,12 @@
 #pragma once
 #include "kernels_plane.cuh"
 
+#ifndef MFHN_BULK_DEFAULT_OCC
+#define MFHN_BULK_DEFAULT_OCC 5
+#endif
+
 namespace mfhn
 {
-constexpr bool bulk_supported(int n) { return n >= 4 && n <= 6; }
 __host__ __device__ constexpr int round_up_to(int v, int m) { return (v + m - 1) / m * m; }
 constexpr uint32_t bulk_invalid = 0xffffffffu;
 
@@ -190,8 +193,9 @@ __device__ __forceinline__ void bulk_issue(Number *A, const Number *vec, const u
       }
 }
 
-template <int n, typename Number>
-__global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 3)) bulk_cell_kernel(const BulkParams p)
+// OCC = CTAs per SM the register allocation is limited for (4: 128, 5: 96, 6: 80 registers per thread)
+template <int n, typename Number, int OCC = 4>
+__global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, OCC) bulk_cell_kernel(const BulkParams p)
 {
   using Cfg = PlaneCfg<n, Number>;
   using B   = BulkCfg<n, Number>;
@@ -272,34 +276,47 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
   Number *cellA = A + c * cs;
   if (any_hn)
     {
+      if (active)
+        {
 #pragma unroll
-      for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+          for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+        }
       __syncwarp();
-      hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t);
+      hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t, active);
 #pragma unroll
       for (int j = 0; j < n * n; ++j) u[j / n][j % n] = cellA[t * ps + j];
       __syncwarp();
     }
 
-  plane_sweeps<n>(u, cellA, t, h);
-  if (any_hn) hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t);
+  plane_sweeps<n>(u, cellA, t, h, active);
+  __syncwarp(); // every lane has read its plane back
+  if (any_hn)
+    {
+      if (active)
+        {
+#pragma unroll
+          for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+        }
+      __syncwarp();
+      hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t, active);
+#pragma unroll
+      for (int j = 0; j < n * n; ++j) u[j / n][j % n] = cellA[t * ps + j];
+      __syncwarp();
+    }
 
   // ---- scatter ---------------------------------------------------------------------------
+  // the results go from registers straight to the staging layout
   bulk_descriptors<n, Number>(p, batch, lane, hexfirst, qfirst);
 #pragma unroll
   for (int r = 0; r < B::R; ++r) g[r] = __ldg(lvp + r * 32);
   {
-    Number r[n * n];
-#pragma unroll
-    for (int j = 0; j < n * n; ++j) r[j] = cellA[t * ps + j];
-    __syncwarp(); // back to the staging layout
     const unsigned info2 = __ldg(p.cinfo + cell); // loaded again instead of living through the sweeps
     if (active && !(info2 >> 31))
       {
         const BulkAddr<n, Number> pos(t, info2);
         Number *S = A + c * B::Ss;
 #pragma unroll
-        for (int j = 0; j < n * n; ++j) S[pos(j % n, j / n)] = r[j];
+        for (int j = 0; j < n * n; ++j) S[pos(j % n, j / n)] = u[j / n][j % n];
       }
   }
   // the widened blocks add into neighbouring vector entries: those staging slots must hold zero
@@ -342,44 +359,26 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 
 }
 
 // ---- host side ------------------------------------------------------------------
-struct BulkHostLayout
+template <int n, typename Number, int OCC>
+void launch_bulk_occ(const BulkParams &p, const unsigned grid, int device, cudaStream_t stream)
 {
-  int n = 0, E = 2;
-  long long n_cells = 0, n_batches = 0;
-  std::vector<uint32_t> bidx, lvidx, cinfo;
-  std::vector<long long> irregular; // cells left to the plane kernel, ascending
-};
-
-struct BulkLayout
-{
-  int n = 0;
-  long long n_cells = 0, n_batches = 0;
-  uint32_t *d_bidx = nullptr, *d_lvidx = nullptr, *d_cinfo = nullptr;
-  std::vector<long long> irregular;
-  bool usable = false; // built and few enough irregular cells
-
-  void free()
-  {
-    cudaFree(d_bidx);
-    cudaFree(d_lvidx);
-    cudaFree(d_cinfo);
-    d_bidx = d_lvidx = d_cinfo = nullptr;
-    usable = false;
-  }
-};
+  using B = BulkCfg<n, Number>;
+  static bool attr[64] = {};
+  if (!attr[device])
+    {
+      cudaError_t e = cudaFuncSetAttribute(bulk_cell_kernel<n, Number, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::smem);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+      attr[device] = true;
+    }
+  bulk_cell_kernel<n, Number, OCC><<<grid, B::warps * 32, B::smem, stream>>>(p);
+}
 
 template <int n, typename Number>
 void launch_bulk_impl(const BulkLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream)
 {
   using Cfg = PlaneCfg<n, Number>;
   using B   = BulkCfg<n, Number>;
-  static bool attr[64] = {};
-  if (!attr[device])
-    {
-      cudaError_t e = cudaFuncSetAttribute(bulk_cell_kernel<n, Number>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::smem);
-      if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-      attr[device] = true;
-    }
+  if (device < 0 || device >= 64) throw std::runtime_error("device ordinal out of range");
   BulkParams p;
   p.bidx              = L.d_bidx;
   p.lvidx             = L.d_lvidx;
@@ -396,7 +395,15 @@ void launch_bulk_impl(const BulkLayout &L, const CellLoopParams &cp, int device,
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + B::warps - 1) / B::warps);
-  bulk_cell_kernel<n, Number><<<grid, B::warps * 32, B::smem, stream>>>(p);
+  // the double-precision kernels of degree >= 4 are register-bound: 5 CTAs (96 registers) measured best on B200
+  constexpr bool reg_bound = sizeof(Number) == 8 && n >= 5;
+  const int occ = occupancy_choice(n, sizeof(Number) == 8, n == 5 ? MFHN_BULK_DEFAULT_OCC : 4); // k = 5: 128 registers measured best
+  if (reg_bound && occ == 5)
+    launch_bulk_occ<n, Number, reg_bound ? 5 : 4>(p, grid, device, stream);
+  else if (reg_bound && occ == 6)
+    launch_bulk_occ<n, Number, reg_bound ? 6 : 4>(p, grid, device, stream);
+  else
+    launch_bulk_occ<n, Number, 4>(p, grid, device, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("bulk kernel launch: ") + cudaGetErrorString(e));
 }

@@ -9,32 +9,13 @@
 // submit_gradient(get_gradient) -> integrate(gradients) -> interpolation^T ->
 // distribute_local_to_global (atomic add).
 #pragma once
+#include "layouts.hpp"
 #include "shape_tables.cuh"
 
 #include <cstdint>
 
 namespace mfhn
 {
-struct CellLoopParams
-{
-  const uint32_t *idx;  // [n_cells][(k+1)^3] lexicographic
-  const uint8_t *masks; // [n_cells]
-  const void *geom;     // Number[n_cells] (h) or Number[n_cells][6] (metric)
-  const void *src;
-  void *dst;
-  long long cell_begin, cell_end;
-  int apply_constraints;
-};
-
-enum GenericVariant
-{
-  GV_QPOINT_CARTESIAN = 0, // collocation gradients, diagonal q-point factor w_q h
-  GV_QPOINT_METRIC    = 1, // collocation gradients, symmetric 3x3 metric per cell
-  GV_SEPARABLE        = 2, // h (K x M x M + M x K x M + M x M x K)
-  GV_QPOINT_GENERAL   = 3  // collocation gradients, symmetric 3x3 coefficient per QUADRATURE POINT
-                           // (JxW J^-1 J^-T, [cell][6][q]): curved cells / high-order mappings
-};
-
 template <int n, int T, bool transpose, typename Number>
 __device__ __forceinline__ void mat_vec(const Number (&in)[n], Number (&out)[n])
 {

@@ -29,8 +29,18 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
+#include <string>
 #include <vector>
+
+#ifndef MFHN_PLANE_DEFAULT_OCC
+#define MFHN_PLANE_DEFAULT_OCC 4
+#endif
+#ifndef MFHN_HN_INLINE
+#define MFHN_HN_INLINE __noinline__
+#endif
+// (-DMFHN_HN_INLINE=__forceinline__ inlines the hanging-node passes into the cell kernels)
 
 namespace mfhn
 {
@@ -55,7 +65,6 @@ struct PlaneCfg
   static constexpr int smem  = warps * smem_per_warp;
 };
 
-constexpr bool plane_supported(int n) { return n >= 2 && n <= 6; }
 
 struct PlaneParams
 {
@@ -66,7 +75,6 @@ struct PlaneParams
   void *dst;
   long long cell_begin, cell_end, batch_begin, batch_end;
   int apply_constraints;
-  cudaTextureObject_t src_tex; // src bound as a linear texture: gathers go through the TEX pipe
   // peer mode (boundary cells of a partitioned operator): ghost entries (index >= n_owned) are read from /
   // added to the OWNER's vectors through peer-mapped pointers over NVLink instead of a local ghost section
   long long n_owned;
@@ -74,139 +82,83 @@ struct PlaneParams
   void *const *ghost_dst;       // [n_ghost] address of the entry in the owner's dst
 };
 
-template <typename Number>
-__device__ __forceinline__ Number tex_fetch(cudaTextureObject_t tex, uint32_t i);
-template <>
-__device__ __forceinline__ double tex_fetch<double>(cudaTextureObject_t tex, uint32_t i)
-{
-  const int2 v = tex1Dfetch<int2>(tex, (int)i);
-  return __hiloint2double(v.y, v.x);
-}
-template <>
-__device__ __forceinline__ float tex_fetch<float>(cudaTextureObject_t tex, uint32_t i)
-{
-  return tex1Dfetch<float>(tex, (int)i);
-}
-
-// ---- even-odd application of a persymmetric matrix --------------------------
+// ---- fast diagonalisation of the Cartesian cell matrix -------------------------
+// With M = T^T T and K = T^T diag(lambda) T (fe1d.hpp)
+//   h (K x M x M + M x K x M + M x M x K) = h (T x T x T)^T diag(lambda_i + lambda_j + lambda_k) (T x T x T):
+// three forward sweeps with T, one scaling, three backward sweeps with T^T -- six one-matrix sweeps, and only
+// ONE array crosses each change of the thread axis.  The rows of T are symmetric / antisymmetric, so a sweep is
+// an even-odd product: (n+1)/2 x (n+1)/2 + n/2 x n/2 multiply-adds per line.
 template <int n, typename Number>
-__device__ __forceinline__ void eo_split(const Number (&x)[n], Number (&xs)[(n + 1) / 2], Number (&xd)[(n + 1) / 2])
+__device__ __forceinline__ void fdm_fwd(const Number (&x)[n], Number (&y)[n]) // y = T x
 {
-  constexpr int h = n / 2;
+  constexpr int h = n / 2, he = (n + 1) / 2;
+  Number xs[he], xd[he];
 #pragma unroll
   for (int j = 0; j < h; ++j)
     {
       xs[j] = x[j] + x[n - 1 - j];
       xd[j] = x[j] - x[n - 1 - j];
     }
-  if (n % 2)
-    {
-      xs[h] = x[h];
-      xd[h] = Number(0);
-    }
-}
-template <int n, int TE, int TO, bool INIT, typename Number>
-__device__ __forceinline__ void eo_mac(const Number (&xs)[(n + 1) / 2], const Number (&xd)[(n + 1) / 2],
-                                       Number (&se)[(n + 1) / 2], Number (&so)[(n + 1) / 2])
-{
-  constexpr int h = n / 2, he = (n + 1) / 2;
+  if (n % 2) xs[h] = x[h];
+  Number r[n];
 #pragma unroll
   for (int i = 0; i < he; ++i)
+    {
+      Number s = Shape<Number>::template eo<n, T_TE>(i * he) * xs[0];
 #pragma unroll
-    for (int j = 0; j < he; ++j)
-      {
-        const Number c = Shape<Number>::template eo<n, TE>(i * he + j);
-        se[i]          = (INIT && j == 0) ? c * xs[j] : se[i] + c * xs[j];
-      }
-#pragma unroll
-  for (int i = 0; i < h; ++i)
-#pragma unroll
-    for (int j = 0; j < h; ++j)
-      {
-        const Number c = Shape<Number>::template eo<n, TO>(i * he + j);
-        so[i]          = (INIT && j == 0) ? c * xd[j] : so[i] + c * xd[j];
-      }
-}
-template <int n, typename Number>
-__device__ __forceinline__ void eo_merge(const Number (&se)[(n + 1) / 2], const Number (&so)[(n + 1) / 2], Number (&y)[n])
-{
-  constexpr int h = n / 2;
+      for (int j = 1; j < he; ++j) s += Shape<Number>::template eo<n, T_TE>(i * he + j) * xs[j];
+      r[i] = s;
+    }
 #pragma unroll
   for (int i = 0; i < h; ++i)
     {
-      y[i]         = se[i] + so[i];
-      y[n - 1 - i] = se[i] - so[i];
-    }
-  if (n % 2) y[h] = se[h];
-}
-
-// p = M x, q = K x
-template <int n, typename Number>
-__device__ __forceinline__ void apply_MK(const Number (&x)[n], Number (&p)[n], Number (&q)[n])
-{
-  if (n >= 4)
-    {
-      Number xs[(n + 1) / 2], xd[(n + 1) / 2], se[(n + 1) / 2], so[(n + 1) / 2];
-      eo_split<n>(x, xs, xd);
-      eo_mac<n, T_ME, T_MO, true>(xs, xd, se, so);
-      eo_merge<n>(se, so, p);
-      eo_mac<n, T_KE, T_KO, true>(xs, xd, se, so);
-      eo_merge<n>(se, so, q);
-    }
-  else
-    {
-      mat_vec<n, T_M, false>(x, p);
-      mat_vec<n, T_K, false>(x, q);
-    }
-}
-// a = M p, b = M q + K p
-template <int n, typename Number>
-__device__ __forceinline__ void apply_M_MK(const Number (&p)[n], const Number (&q)[n], Number (&a)[n], Number (&b)[n])
-{
-  if (n >= 4)
-    {
-      constexpr int he = (n + 1) / 2;
-      Number ps[he], pd[he], qs[he], qd[he], se[he], so[he];
-      eo_split<n>(p, ps, pd);
-      eo_split<n>(q, qs, qd);
-      eo_mac<n, T_ME, T_MO, true>(ps, pd, se, so);
-      eo_merge<n>(se, so, a);
-      eo_mac<n, T_ME, T_MO, true>(qs, qd, se, so);
-      eo_mac<n, T_KE, T_KO, false>(ps, pd, se, so);
-      eo_merge<n>(se, so, b);
-    }
-  else
-    {
-      Number t[n];
-      mat_vec<n, T_M, false>(p, a);
-      mat_vec<n, T_M, false>(q, b);
-      mat_vec<n, T_K, false>(p, t);
+      Number s = Shape<Number>::template eo<n, T_TO>(i * he) * xd[0];
 #pragma unroll
-      for (int i = 0; i < n; ++i) b[i] += t[i];
+      for (int j = 1; j < h; ++j) s += Shape<Number>::template eo<n, T_TO>(i * he + j) * xd[j];
+      r[he + i] = s;
     }
-}
-// r = M b + K a
-template <int n, typename Number>
-__device__ __forceinline__ void apply_Mb_Ka(const Number (&a)[n], const Number (&b)[n], Number (&r)[n])
-{
-  if (n >= 4)
-    {
-      constexpr int he = (n + 1) / 2;
-      Number as[he], ad[he], bs[he], bd[he], se[he], so[he];
-      eo_split<n>(a, as, ad);
-      eo_split<n>(b, bs, bd);
-      eo_mac<n, T_ME, T_MO, true>(bs, bd, se, so);
-      eo_mac<n, T_KE, T_KO, false>(as, ad, se, so);
-      eo_merge<n>(se, so, r);
-    }
-  else
-    {
-      Number t[n];
-      mat_vec<n, T_M, false>(b, r);
-      mat_vec<n, T_K, false>(a, t);
 #pragma unroll
-      for (int i = 0; i < n; ++i) r[i] += t[i];
+  for (int i = 0; i < n; ++i) y[i] = r[i];
+}
+template <int n, typename Number>
+__device__ __forceinline__ void fdm_bwd(const Number (&w)[n], Number (&y)[n]) // y = T^T w
+{
+  constexpr int h = n / 2, he = (n + 1) / 2;
+  Number e[he], o[he];
+#pragma unroll
+  for (int j = 0; j < he; ++j)
+    {
+      Number s = Shape<Number>::template eo<n, T_TE>(j) * w[0];
+#pragma unroll
+      for (int i = 1; i < he; ++i) s += Shape<Number>::template eo<n, T_TE>(i * he + j) * w[i];
+      e[j] = s;
     }
+#pragma unroll
+  for (int j = 0; j < h; ++j)
+    {
+      Number s = Shape<Number>::template eo<n, T_TO>(j) * w[he];
+#pragma unroll
+      for (int i = 1; i < h; ++i) s += Shape<Number>::template eo<n, T_TO>(i * he + j) * w[he + i];
+      o[j] = s;
+    }
+#pragma unroll
+  for (int j = 0; j < h; ++j)
+    {
+      y[j]         = e[j] + o[j];
+      y[n - 1 - j] = e[j] - o[j];
+    }
+  if (n % 2) y[h] = e[h];
+}
+// One line along the cross-thread axis: forward, eigenvalue scaling, backward.  hl = h (lambda_a + lambda_b) of
+// the two other indices; the eigenvalue of the line's own index is a compile-time constant.
+template <int n, typename Number>
+__device__ __forceinline__ void fdm_mid(Number (&v)[n], const Number h, const Number hl)
+{
+  Number w[n];
+  fdm_fwd<n>(v, w);
+#pragma unroll
+  for (int z = 0; z < n; ++z) w[z] *= h * Shape<Number>::template lam<n>(z) + hl;
+  fdm_bwd<n>(w, v);
 }
 
 // In-place hanging-node interpolation (or its transpose) on the cell arrays of
@@ -216,7 +168,7 @@ __device__ __forceinline__ void apply_Mb_Ka(const Number (&a)[n], const Number (
 // cell; the assignment is chosen per cell so that the lines of a constrained
 // face land on n different threads of the same iteration.
 template <int n, bool transpose, typename Number>
-__device__ __forceinline__ void hn_smem(Number *cellA, unsigned face, unsigned edge, unsigned cb, int t)
+__device__ MFHN_HN_INLINE void hn_smem(Number *cellA, unsigned face, unsigned edge, unsigned cb, int t, const bool active = true)
 {
   constexpr int k = n - 1;
   using Cfg = PlaneCfg<n, Number>;
@@ -238,7 +190,8 @@ __device__ __forceinline__ void hn_smem(Number *cellA, unsigned face, unsigned e
           const int i = (first + it) % n; // start with the iteration that holds the whole face
           const int a = f1 ? t : i, b = f1 ? i : t;
           const bool on0 = a == c0, on1 = b == c1;
-          const bool sel = (f0 && on0) || (f1 && on1) || (ed && on0 && on1);
+          // idle lanes mirror an active lane's coordinates: they must not repeat its in-place update
+          const bool sel = active && ((f0 && on0) || (f1 && on1) || (ed && on0 && on1));
           if (sel)
             {
               const int base = d == 0 ? b * Cfg::ps + a * n : d == 1 ? b * Cfg::ps + a : b * n + a;
@@ -268,70 +221,65 @@ __device__ __forceinline__ void decode_mask_kernel_axes(unsigned m, unsigned &fa
   cb   = rot3(cb);
 }
 
-// The seven sweeps of one cell: u = this thread's plane [Y][X] (thread = Z); on return the warp's shared-memory
-// array holds h (K x M x M + M x K x M + M x M x K) u in the layout cellA[Z * ps + Y * n + X] (warp-synchronised).
+// The six sweeps of one cell (fast diagonalisation).  u = this thread's plane [Y][X] (thread = Z); on return u
+// holds h (K x M x M + M x K x M + M x M x K) u in the same layout.  The warp's shared-memory array carries the
+// plane across the two changes of the thread axis (Z -> X -> Z); idle lanes compute along but do not store.
 template <int n, typename Number>
-__device__ __forceinline__ void plane_sweeps(const Number (&u)[n][n], Number *cellA, const int t, const Number h)
+__device__ __forceinline__ void plane_sweeps(Number (&u)[n][n], Number *cellA, const int t, const Number h, const bool active)
 {
   using Cfg = PlaneCfg<n, Number>;
   constexpr int ps = Cfg::ps;
-  // ---- P1: x and y sweeps (thread = Z) ----------------------------------------------
-  // a = M_Y M_X u and b = (M_Y K_X + K_Y M_X) u cross the transpose through the same
-  // shared-memory array one after the other (half the shared memory, more warps per SM)
-  Number az[n][n], bz[n][n]; // P2 operands of this thread: [Y][Z]
-  {
-    Number bb[n][n];
+  // ---- P1 (thread = Z): forward sweeps along X (rows) and Y (columns) ----------------
+#pragma unroll
+  for (int y = 0; y < n; ++y) fdm_fwd<n>(u[y], u[y]);
+#pragma unroll
+  for (int x = 0; x < n; ++x)
     {
-      Number pp[n][n], qq[n][n];
+      Number c[n];
 #pragma unroll
-      for (int y = 0; y < n; ++y) apply_MK<n>(u[y], pp[y], qq[y]);
-#pragma unroll
-      for (int x = 0; x < n; ++x)
+      for (int y = 0; y < n; ++y) c[y] = u[y][x];
+      fdm_fwd<n>(c, c);
+      if (active)
         {
-          Number pc[n], qc[n], a[n], b[n];
 #pragma unroll
-          for (int i = 0; i < n; ++i)
-            {
-              pc[i] = pp[i][x];
-              qc[i] = qq[i][x];
-            }
-          apply_M_MK<n>(pc, qc, a, b);
-#pragma unroll
-          for (int i = 0; i < n; ++i)
-            {
-              cellA[t * ps + i * n + x] = a[i];
-              bb[i][x]                  = b[i];
-            }
+          for (int y = 0; y < n; ++y) cellA[t * ps + y * n + x] = c[y];
         }
     }
-    __syncwarp();
-#pragma unroll
-    for (int y = 0; y < n; ++y)
-#pragma unroll
-      for (int z = 0; z < n; ++z) az[y][z] = cellA[z * ps + y * n + t];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = bb[j / n][j % n];
-    __syncwarp();
-#pragma unroll
-    for (int y = 0; y < n; ++y)
-#pragma unroll
-      for (int z = 0; z < n; ++z) bz[y][z] = cellA[z * ps + y * n + t];
-  }
-  // ---- P2: Z sweep (thread = X) ------------------------------------------------------
+  __syncwarp();
+  // ---- P2 (thread = X): forward along Z, eigenvalue scaling, backward along Z ---------
+  const Number hlt = h * Shape<Number>::template lam<n>(t); // runtime index: one constant-memory load
 #pragma unroll
   for (int y = 0; y < n; ++y)
     {
-      Number r[n];
-      apply_Mb_Ka<n>(az[y], bz[y], r);
+      Number v[n];
 #pragma unroll
-      for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = h * r[z];
+      for (int z = 0; z < n; ++z) v[z] = cellA[z * ps + y * n + t];
+      fdm_mid<n>(v, h, h * Shape<Number>::template lam<n>(y) + hlt);
+      if (active)
+        {
+#pragma unroll
+          for (int z = 0; z < n; ++z) cellA[z * ps + y * n + t] = v[z]; // only this thread read these entries
+        }
     }
   __syncwarp();
+  // ---- P3 (thread = Z): backward sweeps along Y and X ---------------------------------
+#pragma unroll
+  for (int x = 0; x < n; ++x)
+    {
+      Number c[n];
+#pragma unroll
+      for (int y = 0; y < n; ++y) c[y] = cellA[t * ps + y * n + x];
+      fdm_bwd<n>(c, c);
+#pragma unroll
+      for (int y = 0; y < n; ++y) u[y][x] = c[y];
+    }
+#pragma unroll
+  for (int y = 0; y < n; ++y) fdm_bwd<n>(u[y], u[y]);
 }
 
-template <int n, typename Number, bool TEX, bool PEER = false>
-__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 : 3)) plane_cell_kernel(const PlaneParams p)
+// OCC = CTAs per SM the register allocation is limited for (4: 128, 5: 96, 6: 80 registers per thread)
+template <int n, typename Number, bool PEER = false, int OCC = 4>
+__global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, OCC) plane_cell_kernel(const PlaneParams p)
 {
   using Cfg = PlaneCfg<n, Number>;
   constexpr int ps = Cfg::ps, cs = Cfg::cs;
@@ -341,9 +289,8 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
   if (batch >= p.batch_end) return; // warps are independent: no block-level barrier below
   Number *A = reinterpret_cast<Number *>(smem_raw) + (size_t)warp * Cfg::cpw * cs;
 
-  // the 32 - cpw n idle lanes mirror lane - 16 (same loads, same values stored to the same
-  // shared-memory addresses; that lane sits in the other half-warp, so no bank conflict arises),
-  // hence the arithmetic needs no per-lane predicate; they do not scatter
+  // the 32 - cpw n idle lanes mirror lane - 16 (same loads and arithmetic, so the warp needs no per-lane
+  // predicate around the sweeps); they neither store to shared memory nor scatter
   const bool active = lane < Cfg::lanes;
   const int ml = active ? lane : lane - 16;
   const int c = ml / n, t = ml - c * n;
@@ -366,7 +313,7 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
         if (PEER && valid && idx[j] >= (uint32_t)p.n_owned) // remote entry: plain load through the peer mapping
           u[j / n][j % n] = *static_cast<const Number *>(p.ghost_src[idx[j] - (uint32_t)p.n_owned]);
         else
-          u[j / n][j % n] = valid ? (TEX ? tex_fetch<Number>(p.src_tex, idx[j]) : __ldg(src + idx[j])) : Number(0);
+          u[j / n][j % n] = valid ? __ldg(src + idx[j]) : Number(0);
       }
   }
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
@@ -377,18 +324,33 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
   if (any_hn)
     {
       // hanging-node interpolation as in-place directional passes on the shared-memory copy
+      if (active)
+        {
 #pragma unroll
-      for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+          for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+        }
       __syncwarp();
-      hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t);
+      hn_smem<n, false>(cellA, hn_face, hn_edge, hn_cb, t, active);
 #pragma unroll
       for (int j = 0; j < n * n; ++j) u[j / n][j % n] = cellA[t * ps + j];
       __syncwarp();
     }
 
-  plane_sweeps<n>(u, cellA, t, h);
-  if (any_hn) hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t);
-  // ---- P3: scatter (thread = z) --------------------------------------------------------
+  plane_sweeps<n>(u, cellA, t, h, active);
+  if (any_hn)
+    {
+      __syncwarp(); // every lane has read its plane back
+      if (active)
+        {
+#pragma unroll
+          for (int j = 0; j < n * n; ++j) cellA[t * ps + j] = u[j / n][j % n];
+        }
+      __syncwarp();
+      hn_smem<n, true>(cellA, hn_face, hn_edge, hn_cb, t, active);
+#pragma unroll
+      for (int j = 0; j < n * n; ++j) u[j / n][j % n] = cellA[t * ps + j];
+    }
+  // ---- P3: scatter (thread = z), straight from registers --------------------------------
   if (active && valid)
     {
 #pragma unroll
@@ -396,49 +358,42 @@ __global__ void __launch_bounds__(PlaneCfg<n, Number>::warps * 32, (n <= 5 ? 4 :
         {
           const uint32_t g = __ldg(ip + j * 32);
           if (PEER && g >= (uint32_t)p.n_owned) // red over NVLink into the owner's dst
-            atomicAdd(static_cast<Number *>(p.ghost_dst[g - (uint32_t)p.n_owned]), cellA[t * ps + j]);
+            atomicAdd(static_cast<Number *>(p.ghost_dst[g - (uint32_t)p.n_owned]), u[j / n][j % n]);
           else
-            atomicAdd(dst + g, cellA[t * ps + j]);
+            atomicAdd(dst + g, u[j / n][j % n]);
         }
     }
 }
 
 // ---- host side ------------------------------------------------------------------
-struct PlaneLayout
+// CTAs per SM to compile for: the double-precision kernels of degree >= 4 are register-bound, the others fit 4+ CTAs anyway
+inline int occupancy_choice(const int n, const bool f64, const int fallback)
 {
-  int n = 0;
-  long long n_cells = 0, n_batches = 0;
-  uint32_t *d_pidx = nullptr;
+  const char *e  = std::getenv("MFHN_OCC"); // experiments only (read per launch so that one process can compare)
+  const int env = e ? std::atoi(e) : 0;
+  if (!(f64 && n >= 5)) return 4;
+  return env >= 4 && env <= 6 ? env : fallback;
+}
 
-  void free()
-  {
-    cudaFree(d_pidx);
-    d_pidx = nullptr;
-  }
-  void build(int n_, long long n_cells_, const uint32_t *idx);
-};
-
-struct PeerTables
-{
-  long long n_owned           = 0;
-  const void *const *ghost_src = nullptr;
-  void *const *ghost_dst       = nullptr;
-};
-
-template <int n, typename Number>
-void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex,
-                       const PeerTables *peer = nullptr)
+template <int n, typename Number, bool PEER, int OCC>
+void launch_plane_occ(const PlaneParams &p, const unsigned grid, int device, cudaStream_t stream)
 {
   using Cfg = PlaneCfg<n, Number>;
   static bool attr[64] = {};
   if (!attr[device])
     {
-      cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
+      cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, PEER, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
       if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       attr[device] = true;
     }
+  plane_cell_kernel<n, Number, PEER, OCC><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+}
+
+template <int n, typename Number>
+void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, const PeerTables *peer = nullptr)
+{
+  using Cfg = PlaneCfg<n, Number>;
+  if (device < 0 || device >= 64) throw std::runtime_error("device ordinal out of range");
   PlaneParams p;
   p.pidx              = L.d_pidx;
   p.masks             = cp.masks;
@@ -450,38 +405,31 @@ void launch_plane_impl(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.batch_begin       = cp.cell_begin / Cfg::cpw;
   p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
-  p.src_tex           = tex;
   p.n_owned           = peer ? peer->n_owned : 0;
   p.ghost_src         = peer ? peer->ghost_src : nullptr;
   p.ghost_dst         = peer ? peer->ghost_dst : nullptr;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + Cfg::warps - 1) / Cfg::warps);
+  constexpr bool reg_bound = sizeof(Number) == 8 && n >= 5;
+  const int occ = occupancy_choice(n, sizeof(Number) == 8, MFHN_PLANE_DEFAULT_OCC);
   if (peer)
-    {
-      static bool pattr[64] = {};
-      if (!pattr[device])
-        {
-          cudaError_t e = cudaFuncSetAttribute(plane_cell_kernel<n, Number, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
-          if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-          pattr[device] = true;
-        }
-      plane_cell_kernel<n, Number, false, true><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
-    }
-  else if (tex)
-    plane_cell_kernel<n, Number, true><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+    launch_plane_occ<n, Number, true, 4>(p, grid, device, stream);
+  else if (reg_bound && occ == 5)
+    launch_plane_occ<n, Number, false, reg_bound ? 5 : 4>(p, grid, device, stream);
+  else if (reg_bound && occ == 6)
+    launch_plane_occ<n, Number, false, reg_bound ? 6 : 4>(p, grid, device, stream);
   else
-    plane_cell_kernel<n, Number, false><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+    launch_plane_occ<n, Number, false, 4>(p, grid, device, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("plane kernel launch: ") + cudaGetErrorString(e));
 }
 
 template <int n, typename Number>
-void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, cudaTextureObject_t tex,
-                  const PeerTables *peer = nullptr)
+void launch_plane(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, const PeerTables *peer = nullptr)
 {
   if constexpr (plane_supported(n))
-    launch_plane_impl<n, Number>(L, cp, device, stream, tex, peer);
+    launch_plane_impl<n, Number>(L, cp, device, stream, peer);
   else
     throw std::runtime_error("plane kernel not available for this degree");
 }

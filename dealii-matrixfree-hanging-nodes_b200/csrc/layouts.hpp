@@ -1,0 +1,107 @@
+// Host-side descriptions shared by the kernel translation units and the operator object (op.cu): cell-loop
+// parameters, the device layouts of the cell kernels and the non-template launch entry points.  Every kernel
+// family lives in its own translation unit (k_*.cu) so that the library builds in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+namespace mfhn
+{
+struct CellLoopParams
+{
+  const uint32_t *idx;  // [n_cells][(k+1)^3] lexicographic
+  const uint8_t *masks; // [n_cells]
+  const void *geom;     // Number[n_cells] (h), Number[n_cells][6] (metric) or Number[n_cells][6][(k+1)^3]
+  const void *src;
+  void *dst;
+  long long cell_begin, cell_end;
+  int apply_constraints;
+};
+
+enum GenericVariant
+{
+  GV_QPOINT_CARTESIAN = 0, // collocation gradients, diagonal q-point factor w_q h
+  GV_QPOINT_METRIC    = 1, // collocation gradients, symmetric 3x3 metric per cell
+  GV_SEPARABLE        = 2, // h (K x M x M + M x K x M + M x M x K)
+  GV_QPOINT_GENERAL   = 3  // collocation gradients, symmetric 3x3 coefficient per QUADRATURE POINT
+                           // (JxW J^-1 J^-T, [cell][6][q]): curved cells / high-order mappings
+};
+
+// warp-interleaved index layout of the plane kernels: [n_batches][n*n][32]
+struct PlaneLayout
+{
+  int n = 0;
+  long long n_cells = 0, n_batches = 0;
+  uint32_t *d_pidx = nullptr;
+
+  void free()
+  {
+    cudaFree(d_pidx);
+    d_pidx = nullptr;
+  }
+  void build(int n_, long long n_cells_, const uint32_t *idx); // op.cu
+};
+
+// peer mode (boundary cells of a partitioned operator): ghost entries are read from / added to the OWNER's vectors
+struct PeerTables
+{
+  long long n_owned           = 0;
+  const void *const *ghost_src = nullptr;
+  void *const *ghost_dst       = nullptr;
+};
+
+struct BulkHostLayout
+{
+  int n = 0, E = 2;
+  long long n_cells = 0, n_batches = 0;
+  std::vector<uint32_t> bidx, lvidx, cinfo;
+  std::vector<long long> irregular; // cells left to the plane kernel, ascending
+};
+
+struct BulkLayout
+{
+  int n = 0;
+  long long n_cells = 0, n_batches = 0;
+  uint32_t *d_bidx = nullptr, *d_lvidx = nullptr, *d_cinfo = nullptr;
+  std::vector<long long> irregular;
+  bool usable = false; // built and few enough irregular cells
+
+  void free()
+  {
+    cudaFree(d_bidx);
+    cudaFree(d_lvidx);
+    cudaFree(d_cinfo);
+    d_bidx = d_lvidx = d_cinfo = nullptr;
+    usable = false;
+  }
+};
+
+struct BaselineArrays
+{
+  uint32_t *l2g = nullptr;
+  void *invjac = nullptr, *jxw = nullptr;
+};
+
+constexpr bool plane_supported(int n) { return n >= 2 && n <= 6; }      // register-tiled plane kernel
+constexpr bool plane_smem_supported(int n) { return n >= 2 && n <= 9; } // plane in shared memory
+constexpr bool bulk_supported(int n) { return n >= 4 && n <= 6; }
+
+// ---- launch entry points (degree = k, number = MFHN_F64 / MFHN_F32); they throw std::runtime_error ----
+// k_generic_*.cu
+void run_generic(int degree, int number, int variant, bool diag, const CellLoopParams &p, int device, cudaStream_t stream);
+// k_plane.cu: register-tiled kernel for k <= 5, shared-memory plane kernel above; peer != nullptr: k <= 5 only
+void run_plane(int degree, int number, const PlaneLayout &L, const CellLoopParams &p, int device, cudaStream_t stream, const PeerTables *peer);
+// k_bulk.cu
+void run_bulk(int degree, int number, const BulkLayout &L, const CellLoopParams &p, int device, cudaStream_t stream);
+void bulk_analyze(BulkHostLayout &L, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx);
+long long bulk_verify(const BulkHostLayout &L, int number, const uint32_t *idx);
+// k_misc.cu
+void run_baseline(int degree, int number, BaselineArrays &arrays, const uint32_t *d_idx, const void *d_h, long long n_cells, const CellLoopParams &p,
+                  int device, cudaStream_t stream);
+void run_hn_only(int degree, int number, void *values, const uint8_t *d_masks, long long n_cells, int transpose, cudaStream_t stream);
+double run_fma_bench(int number, int iters);
+void run_pack(int number, void *buffer, const void *vec, const int32_t *idx, long long n, cudaStream_t stream);
+void run_unpack_add(int number, void *vec, const void *buffer, const int32_t *idx, long long n, bool atomic, cudaStream_t stream);
+} // namespace mfhn

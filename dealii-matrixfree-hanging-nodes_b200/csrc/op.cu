@@ -4,13 +4,8 @@
 #include "../../include/mfhn.h"
 #include "error.hpp"
 #include "fe1d.hpp"
-#include "kernels_generic.cuh"
-#include "kernels_plane.cuh"
-#include "kernels_bulk.cuh"
-#include "kernels_patch.cuh"
-#include "kernels_plane_smem.cuh"
+#include "layouts.hpp"
 #include "dist.cuh"
-#include "kernels_baseline.cuh"
 #include "octree.hpp"
 
 #include <cuda_runtime.h>
@@ -38,63 +33,6 @@ namespace mfhn
 
 namespace
 {
-std::mutex g_table_mutex;
-bool g_tables_uploaded[64] = {};
-
-void upload_tables(int device)
-{
-  std::lock_guard<std::mutex> lock(g_table_mutex);
-  if (device >= 0 && device < 64 && g_tables_uploaded[device]) return;
-  static ShapeTables<double> hd;
-  static ShapeTables<float> hf;
-  std::memset(&hd, 0, sizeof(hd));
-  for (int k = 1; k <= 8; ++k)
-    {
-      const Shape1D s = make_shape(k);
-      const int n = k + 1, h = n / 2, he = (n + 1) / 2;
-      auto &t = hd.full[k - 1];
-      for (int i = 0; i < n * n; ++i)
-        {
-          t[T_S][i]  = s.S[i];
-          t[T_DC][i] = s.Dc[i];
-          t[T_W0][i] = s.W[0][i];
-          t[T_M][i]  = s.M[i];
-          t[T_K][i]  = s.K[i];
-        }
-      for (int i = 0; i < n; ++i) hd.qw[k - 1][i] = s.qw[i];
-      // even-odd halves of the persymmetric M and K: E = (A[i][j] + A[i][n-1-j]) / 2 (middle
-      // column: A[i][m]), O = (A[i][j] - A[i][n-1-j]) / 2
-      if (he <= MAX_HE)
-        for (int which = 0; which < 2; ++which)
-          {
-            const std::vector<double> &A = which == 0 ? s.M : s.K;
-            double *E = hd.eo[k - 1][which == 0 ? T_ME : T_KE], *O = hd.eo[k - 1][which == 0 ? T_MO : T_KO];
-            for (int i = 0; i < he; ++i)
-              for (int j = 0; j < he; ++j)
-                {
-                  if (j < h)
-                    {
-                      E[i * he + j] = 0.5 * (A[i * n + j] + A[i * n + (n - 1 - j)]);
-                      O[i * he + j] = 0.5 * (A[i * n + j] - A[i * n + (n - 1 - j)]);
-                    }
-                  else
-                    {
-                      E[i * he + j] = A[i * n + j];
-                      O[i * he + j] = 0;
-                    }
-                }
-          }
-    }
-  {
-    const double *ps = reinterpret_cast<const double *>(&hd);
-    float *pf        = reinterpret_cast<float *>(&hf);
-    for (size_t i = 0; i < sizeof(hd) / sizeof(double); ++i) pf[i] = (float)ps[i];
-  }
-  CUDA_CHECK(cudaMemcpyToSymbol(c_shape_d, &hd, sizeof(hd)));
-  CUDA_CHECK(cudaMemcpyToSymbol(c_shape_f, &hf, sizeof(hf)));
-  if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
-}
-
 template <typename T>
 T *to_device(const std::vector<T> &h)
 {
@@ -127,28 +65,6 @@ void PlaneLayout::build(int n_, long long n_cells_, const uint32_t *idx)
 }
 
 // ---- bulk-copy layout -------------------------------------------------------------
-static void bulk_analyze(BulkHostLayout &L, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx)
-{
-  const bool f64 = number == MFHN_F64;
-  switch (n)
-    {
-      case 4: f64 ? bulk_analyze_impl<4, double>(L, n_cells, n_vec, idx) : bulk_analyze_impl<4, float>(L, n_cells, n_vec, idx); break;
-      case 5: f64 ? bulk_analyze_impl<5, double>(L, n_cells, n_vec, idx) : bulk_analyze_impl<5, float>(L, n_cells, n_vec, idx); break;
-      case 6: f64 ? bulk_analyze_impl<6, double>(L, n_cells, n_vec, idx) : bulk_analyze_impl<6, float>(L, n_cells, n_vec, idx); break;
-      default: throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
-    }
-}
-static long long bulk_verify(const BulkHostLayout &L, int number, const uint32_t *idx)
-{
-  const bool f64 = number == MFHN_F64;
-  switch (L.n)
-    {
-      case 4: return f64 ? bulk_verify_impl<4, double>(L, idx) : bulk_verify_impl<4, float>(L, idx);
-      case 5: return f64 ? bulk_verify_impl<5, double>(L, idx) : bulk_verify_impl<5, float>(L, idx);
-      case 6: return f64 ? bulk_verify_impl<6, double>(L, idx) : bulk_verify_impl<6, float>(L, idx);
-      default: throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
-    }
-}
 // more irregular cells than this: the layout does not fit the numbering, the plane kernel runs everything
 constexpr long long bulk_max_irregular = 32;
 
@@ -167,117 +83,6 @@ static void bulk_build(BulkLayout &B, int n, int number, long long n_cells, long
   B.d_cinfo = to_device(L.cinfo);
 }
 
-template <int n, typename Number>
-static int patch_slot(int s, int j)
-{
-  using Cfg = PatchCfg<n, Number>;
-  return Cfg::slot(s, j % n, (j / n) % n, j / (n * n));
-}
-template <typename Number>
-static int patch_slot_n(int n, int s, int j)
-{
-  switch (n)
-    {
-      case 2: return patch_slot<2, Number>(s, j);
-      case 3: return patch_slot<3, Number>(s, j);
-      case 4: return patch_slot<4, Number>(s, j);
-      case 5: return patch_slot<5, Number>(s, j);
-      case 6: return patch_slot<6, Number>(s, j);
-      default: throw InvalidArgument("patch kernel not available for this degree");
-    }
-}
-
-void PatchLayout::build(int n_, int number_, long long n_cells_, const uint32_t *idx)
-{
-  n       = n_;
-  number  = number_;
-  n_cells = n_cells_;
-  const int cpw = 32 / n, n2 = n * n, n3 = n2 * n, ent_stride = cpw * n3;
-  const int rounds = (ent_stride + 31) / 32, u_stride = rounds * 32;
-  n_patches = (n_cells + cpw - 1) / cpw;
-  const size_t np = (size_t)std::max<long long>(n_patches, 1);
-  std::vector<uint32_t> uidx(np * u_stride, 0u);
-  std::vector<uint16_t> lidx(np * n2 * 32, 0);
-  std::vector<uint16_t> ent(np * ent_stride, 0);
-  std::vector<PatchInfo> info(np);
-  long long total = 0;
-#pragma omp parallel reduction(+ : total)
-  {
-    struct Entry { uint32_t g; uint16_t slot, lpos; }; // lpos = plane slot * 32 + lane
-    std::vector<Entry> entries;
-    struct Group { uint32_t g; int first, count; };
-    std::vector<Group> groups;
-#pragma omp for schedule(dynamic, 64)
-    for (long long pt = 0; pt < n_patches; ++pt)
-      {
-        const long long cb = pt * cpw;
-        const int nc       = (int)std::min<long long>(cpw, n_cells - cb);
-        entries.clear();
-        for (int s = 0; s < nc; ++s)
-          for (int j = 0; j < n3; ++j)
-            {
-              const int x = j % n, y = (j / n) % n, z = j / n2;
-              const int slot = number == MFHN_F64 ? patch_slot_n<double>(n, s, j) : patch_slot_n<float>(n, s, j);
-              // thread t = x of cell s sits in lane s n + x; its plane slot is y + n z (kernel axes (X,Y,Z) = (y,z,x))
-              entries.push_back(Entry{idx[(cb + s) * n3 + j], (uint16_t)slot, (uint16_t)((y + n * z) * 32 + s * n + x)});
-            }
-        std::sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.g < b.g; });
-        groups.clear();
-        for (int i = 0; i < (int)entries.size();)
-          {
-            int j = i;
-            while (j < (int)entries.size() && entries[j].g == entries[i].g) ++j;
-            // multiplicities other than 1, 2, 4, 8 are split (3 = 2 + 1, ...): such a DoF is listed more
-            // than once, i.e. read twice and sent two REDs
-            int first = i, left = j - i;
-            while (left > 0)
-              {
-                const int piece = left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
-                groups.push_back(Group{entries[i].g, first, piece});
-                first += piece;
-                left -= piece;
-              }
-            i = j;
-          }
-        // classes by multiplicity (uniform trip counts), ascending address inside a class
-        std::stable_sort(groups.begin(), groups.end(), [](const Group &a, const Group &b) { return a.count < b.count; });
-        PatchInfo &pi = info[pt];
-        pi.n_unique   = (unsigned short)groups.size();
-        pi.pad[0] = pi.pad[1] = pi.pad[2] = 0;
-        for (int m = 0; m < N_CLASSES; ++m) pi.count[m] = 0;
-        for (const Group &g : groups) ++pi.count[g.count == 1 ? 0 : g.count == 2 ? 1 : g.count == 4 ? 2 : 3];
-        uint32_t *u = uidx.data() + pt * u_stride;
-        uint16_t *l = lidx.data() + pt * (size_t)n2 * 32;
-        uint16_t *e = ent.data() + pt * (size_t)ent_stride;
-        size_t gi = 0;
-        int ebase = 0;
-        for (int ci = 0; ci < N_CLASSES; ++ci)
-          {
-            const int m = 1 << ci, cnt = pi.count[ci];
-            for (int i = 0; i < cnt; ++i, ++gi)
-              {
-                u[gi] = groups[gi].g;
-                for (int q = 0; q < m; ++q)
-                  {
-                    const Entry &en        = entries[groups[gi].first + q];
-                    e[ebase + q * cnt + i] = en.slot;
-                    l[en.lpos]             = (uint16_t)gi;
-                  }
-              }
-            ebase += m * cnt;
-          }
-        for (size_t i = groups.size(); i < (size_t)u_stride; ++i) u[i] = groups.empty() ? 0u : groups.back().g; // padding: valid address
-        total += (long long)groups.size();
-      }
-  }
-  unique_per_cell = n_cells > 0 ? (double)total / (double)n_cells : 0;
-  index_bytes     = total * 4 + n_patches * (long long)n2 * 64 + n_cells * (long long)n3 * 2 + n_patches * (long long)sizeof(PatchInfo);
-  d_patches       = to_device(info);
-  d_uidx          = to_device(uidx);
-  d_lidx          = to_device(lidx);
-  d_ent           = to_device(ent);
-}
-
 struct Operator
 {
   int degree = 0, number = 0, device = 0, geometry_type = 0;
@@ -285,48 +90,13 @@ struct Operator
   long long n_cells = 0, n_owned = 0, n_ghost = 0, n_cells_hn = 0;
   uint32_t *d_idx = nullptr;    // reference layout [cell][lexicographic]
   uint8_t *d_masks = nullptr;
-  void *d_geom = nullptr;       // Number h[cell] or Number G[cell][6]
-  PlaneLayout plane;            // warp-interleaved layout of the register-tiled kernel
-  PatchLayout patch;            // sorted-unique / CSR layout of the patch kernel
+  void *d_geom = nullptr;       // Number h[cell], Number G[cell][6] or Number G[cell][6][q]
+  PlaneLayout plane;            // warp-interleaved layout of the plane kernels
   BulkLayout bulk;              // block descriptors of the bulk-copy kernel (degrees 3..5)
-  // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use: 84 B per padded slot)
-  uint32_t *d_base_l2g = nullptr;
-  void *d_base_invjac = nullptr, *d_base_jxw = nullptr;
-  int base_pad = 0;
+  BaselineArrays baseline;      // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use)
   std::vector<long long> segments;
   long long launches = 0;
   void *d_stage_src[2] = {nullptr, nullptr}, *d_stage_dst[2] = {nullptr, nullptr}; // device staging of the host-vector entry point (2 slots)
-  // src vectors bound as linear textures (gathers through the TEX pipe), cached per pointer
-  int use_texture = 0; // measured: no gain over plain loads (profiles/), kept as a switch (MFHN_TEXTURE=1)
-  std::vector<std::pair<const void *, cudaTextureObject_t>> tex_cache;
-  cudaTextureObject_t texture_for(const void *src)
-  {
-    if (!use_texture) return 0;
-    for (auto &e : tex_cache)
-      if (e.first == src) return e.second;
-    const long long nvec = n_owned + n_ghost;
-    cudaResourceDesc rd{};
-    rd.resType                = cudaResourceTypeLinear;
-    rd.res.linear.devPtr      = const_cast<void *>(src);
-    rd.res.linear.desc        = number == MFHN_F64 ? cudaCreateChannelDesc<int2>() : cudaCreateChannelDesc<float>();
-    rd.res.linear.sizeInBytes = (size_t)nvec * (number == MFHN_F64 ? 8 : 4);
-    cudaTextureDesc td{};
-    td.readMode = cudaReadModeElementType;
-    cudaTextureObject_t t = 0;
-    if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess)
-      {
-        cudaGetLastError(); // vector too long for a linear texture: fall back to plain loads
-        use_texture = 0;
-        return 0;
-      }
-    if (tex_cache.size() >= 16)
-      {
-        cudaDestroyTextureObject(tex_cache.front().second);
-        tex_cache.erase(tex_cache.begin());
-      }
-    tex_cache.emplace_back(src, t);
-    return t;
-  }
 
   ~Operator()
   {
@@ -338,104 +108,34 @@ struct Operator
         cudaFree(d_stage_src[i]);
         cudaFree(d_stage_dst[i]);
       }
-    for (auto &e : tex_cache) cudaDestroyTextureObject(e.second);
-    cudaFree(d_base_l2g);
-    cudaFree(d_base_invjac);
-    cudaFree(d_base_jxw);
+    cudaFree(baseline.l2g);
+    cudaFree(baseline.invjac);
+    cudaFree(baseline.jxw);
     plane.free();
-    patch.free();
     bulk.free();
   }
 };
 
 // ---------------------------------------------------------------------------
-template <int n, typename Number, int V, bool DIAG = false>
-void launch_generic(const Operator &op, const CellLoopParams &p, cudaStream_t stream)
+int generic_variant(const Operator &op, int kernel)
 {
-  using Cfg           = GenericCfg<n>;
-  const size_t smem   = (size_t)Cfg::cpb * generic_n_arrays<V>() * Cfg::cs * sizeof(Number);
-  static bool attr[64] = {};
-  if (smem > 48 * 1024 && !attr[op.device])
-    {
-      CUDA_CHECK(cudaFuncSetAttribute(generic_cell_kernel<n, Number, V, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[op.device] = true;
-    }
-  const long long nc = p.cell_end - p.cell_begin;
-  if (nc <= 0) return;
-  const unsigned grid = (unsigned)((nc + Cfg::cpb - 1) / Cfg::cpb);
-  generic_cell_kernel<n, Number, V, DIAG><<<grid, Cfg::threads, smem, stream>>>(p);
-  CUDA_CHECK(cudaGetLastError());
+  if (op.geometry_type == MFHN_GEOM_AFFINE) return GV_QPOINT_METRIC;
+  if (op.geometry_type == MFHN_GEOM_GENERAL) return GV_QPOINT_GENERAL;
+  return kernel == MFHN_KERNEL_SEPARABLE ? GV_SEPARABLE : GV_QPOINT_CARTESIAN;
 }
 
-// diagonal of the operator (for point-Jacobi): Cartesian cells through the separable form, affine through the q-point form
-template <int n, typename Number>
-void launch_diagonal_n(Operator &op, const CellLoopParams &p, cudaStream_t stream)
-{
-  if (op.geometry_type == MFHN_GEOM_AFFINE)
-    launch_generic<n, Number, GV_QPOINT_METRIC, true>(op, p, stream);
-  else if (op.geometry_type == MFHN_GEOM_GENERAL)
-    launch_generic<n, Number, GV_QPOINT_GENERAL, true>(op, p, stream);
-  else
-    launch_generic<n, Number, GV_SEPARABLE, true>(op, p, stream);
-  ++op.launches;
-}
-template <typename Number>
+// diagonal of the operator (for point-Jacobi): Cartesian cells through the separable form, affine / general through the q-point form
 void launch_diagonal(Operator &op, const CellLoopParams &p, cudaStream_t stream)
 {
-  switch (op.degree)
-    {
-      case 1: launch_diagonal_n<2, Number>(op, p, stream); break;
-      case 2: launch_diagonal_n<3, Number>(op, p, stream); break;
-      case 3: launch_diagonal_n<4, Number>(op, p, stream); break;
-      case 4: launch_diagonal_n<5, Number>(op, p, stream); break;
-      case 5: launch_diagonal_n<6, Number>(op, p, stream); break;
-      case 6: launch_diagonal_n<7, Number>(op, p, stream); break;
-      case 7: launch_diagonal_n<8, Number>(op, p, stream); break;
-      case 8: launch_diagonal_n<9, Number>(op, p, stream); break;
-      default: throw InvalidArgument("unsupported degree");
-    }
+  run_generic(op.degree, op.number, op.geometry_type == MFHN_GEOM_CARTESIAN ? GV_SEPARABLE : generic_variant(op, MFHN_KERNEL_QPOINT), true, p, op.device, stream);
+  ++op.launches;
 }
 
-template <int n, typename Number>
-void launch_baseline(Operator &op, const CellLoopParams &p, cudaStream_t stream)
-{
-  using Cfg = BaselineCfg<n>;
-  if (!op.d_base_l2g)
-    {
-      const size_t slots = (size_t)std::max<long long>(op.n_cells, 1) * Cfg::pad;
-      CUDA_CHECK(cudaMalloc(&op.d_base_l2g, slots * sizeof(uint32_t)));
-      CUDA_CHECK(cudaMalloc(&op.d_base_invjac, slots * 9 * sizeof(Number)));
-      CUDA_CHECK(cudaMalloc(&op.d_base_jxw, slots * sizeof(Number)));
-      op.base_pad = Cfg::pad;
-      if (op.n_cells > 0)
-        baseline_setup_kernel<n, Number><<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(
-          op.d_base_l2g, (Number *)op.d_base_invjac, (Number *)op.d_base_jxw, op.d_idx, (const Number *)op.d_geom, op.n_cells, Cfg::pad);
-      CUDA_CHECK(cudaGetLastError());
-    }
-  BaselineParams b;
-  b.local_to_global   = op.d_base_l2g;
-  b.inv_jacobian      = op.d_base_invjac;
-  b.JxW               = op.d_base_jxw;
-  b.masks             = p.masks;
-  b.src               = p.src;
-  b.dst               = p.dst;
-  b.n_cells           = op.n_cells;
-  b.cell_begin        = p.cell_begin;
-  b.cell_end          = p.cell_end;
-  b.pad               = Cfg::pad;
-  b.apply_constraints = p.apply_constraints;
-  const long long nc  = p.cell_end - p.cell_begin;
-  if (nc <= 0) return;
-  baseline_kernel<n, Number><<<(unsigned)((nc + Cfg::cpb - 1) / Cfg::cpb), Cfg::n3 * Cfg::cpb, 0, stream>>>(b);
-  CUDA_CHECK(cudaGetLastError());
-}
-
-template <int n, typename Number>
-void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
+void launch_kernel(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
 {
   if (kernel == MFHN_KERNEL_BASELINE)
     {
-      launch_baseline<n, Number>(op, p, stream);
+      run_baseline(op.degree, op.number, op.baseline, op.d_idx, op.d_geom, op.n_cells, p, op.device, stream);
       ++op.launches;
       return;
     }
@@ -443,7 +143,7 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
     {
       // the bulk-copy kernel takes whole warp batches; the (at most cpw - 1) cells at either end of an unaligned
       // range and the cells that do not show the block pattern (at most bulk_max_irregular) go to the plane kernel
-      constexpr long long cpw = PlaneCfg<n, Number>::cpw;
+      const long long cpw = 32 / (op.degree + 1);
       // (the last batch of the mesh may be incomplete: its missing cells are marked in the layout)
       const long long b0 = (p.cell_begin + cpw - 1) / cpw * cpw;
       const long long b1 = p.cell_end == op.n_cells ? (op.n_cells + cpw - 1) / cpw * cpw : p.cell_end / cpw * cpw;
@@ -452,7 +152,7 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
         CellLoopParams q = p;
         q.cell_begin     = cb;
         q.cell_end       = ce;
-        launch_plane<n, Number>(op.plane, q, op.device, stream, 0);
+        run_plane(op.degree, op.number, op.plane, q, op.device, stream, nullptr);
         ++op.launches;
       };
       if (b1 <= b0)
@@ -465,44 +165,17 @@ void launch_n(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t st
         CellLoopParams q = p;
         q.cell_begin     = b0;
         q.cell_end       = b1;
-        launch_bulk<n, Number>(op.bulk, q, op.device, stream);
+        run_bulk(op.degree, op.number, op.bulk, q, op.device, stream);
       }
       plane_part(b1, p.cell_end);
       for (const long long c : op.bulk.irregular)
         if (c >= b0 && c < std::min(b1, p.cell_end)) plane_part(c, c + 1);
     }
-  else if (kernel == MFHN_KERNEL_PATCH)
-    launch_patch<n, Number>(op.patch, p, op.device, stream);
-  else if (kernel == MFHN_KERNEL_PLANE && plane_supported(n))
-    launch_plane<n, Number>(op.plane, p, op.device, stream, op.texture_for(p.src));
-  else if (kernel == MFHN_KERNEL_PLANE) // degrees 6..8: plane in shared memory
-    launch_plane_smem<n, Number>(op.plane, p, op.device, stream);
-  else if (op.geometry_type == MFHN_GEOM_AFFINE)
-    launch_generic<n, Number, GV_QPOINT_METRIC>(op, p, stream);
-  else if (op.geometry_type == MFHN_GEOM_GENERAL)
-    launch_generic<n, Number, GV_QPOINT_GENERAL>(op, p, stream);
-  else if (kernel == MFHN_KERNEL_SEPARABLE)
-    launch_generic<n, Number, GV_SEPARABLE>(op, p, stream);
+  else if (kernel == MFHN_KERNEL_PLANE)
+    run_plane(op.degree, op.number, op.plane, p, op.device, stream, nullptr);
   else
-    launch_generic<n, Number, GV_QPOINT_CARTESIAN>(op, p, stream);
+    run_generic(op.degree, op.number, generic_variant(op, kernel), false, p, op.device, stream);
   ++op.launches;
-}
-
-template <typename Number>
-void launch_number(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
-{
-  switch (op.degree)
-    {
-      case 1: launch_n<2, Number>(op, kernel, p, stream); break;
-      case 2: launch_n<3, Number>(op, kernel, p, stream); break;
-      case 3: launch_n<4, Number>(op, kernel, p, stream); break;
-      case 4: launch_n<5, Number>(op, kernel, p, stream); break;
-      case 5: launch_n<6, Number>(op, kernel, p, stream); break;
-      case 6: launch_n<7, Number>(op, kernel, p, stream); break;
-      case 7: launch_n<8, Number>(op, kernel, p, stream); break;
-      case 8: launch_n<9, Number>(op, kernel, p, stream); break;
-      default: throw InvalidArgument("unsupported degree");
-    }
 }
 
 int resolve_kernel(const Operator &op)
@@ -520,11 +193,9 @@ int resolve_kernel(const Operator &op)
   if (kernel == MFHN_KERNEL_BULK && !bulk_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
   if (kernel == MFHN_KERNEL_BULK && op.geometry_type == MFHN_GEOM_CARTESIAN && !op.bulk.usable)
     throw InvalidArgument("MFHN_KERNEL_BULK: the DoF numbering does not show contiguous cell-interior / face blocks");
-  if (kernel == MFHN_KERNEL_PATCH && !plane_supported(op.degree + 1))
-    throw NotImplemented("MFHN_KERNEL_PATCH is not available for this degree");
-  if (kernel == MFHN_KERNEL_PATCH && op.patch.d_uidx == nullptr)
-    throw InvalidArgument("the patch layout is built only when the operator is created with MFHN_KERNEL_PATCH");
-  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_PATCH || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
+  if (kernel == MFHN_KERNEL_PATCH)
+    throw NotImplemented("MFHN_KERNEL_PATCH (sorted-unique patch gather, round 1) was measured slower than the plane kernel and has been removed");
+  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
   if (kernel == MFHN_KERNEL_BASELINE && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("the baseline kernel is set up for Cartesian cells");
@@ -551,10 +222,7 @@ void op_vmult_range(Operator &op, void *dst, const void *src, cudaStream_t strea
         throw InvalidArgument("MFHN_KERNEL_BULK needs 16-byte aligned vectors (use MFHN_KERNEL_PLANE for unaligned views)");
       kernel = MFHN_KERNEL_PLANE; // AUTO: unaligned views take the plane kernel
     }
-  if (op.number == MFHN_F64)
-    launch_number<double>(op, kernel, p, stream);
-  else
-    launch_number<float>(op, kernel, p, stream);
+  launch_kernel(op, kernel, p, stream);
 }
 
 Operator *op_create(const mfhn_op_desc &d)
@@ -571,14 +239,12 @@ Operator *op_create(const mfhn_op_desc &d)
     CUDA_CHECK(cudaGetDevice(&device));
   else
     CUDA_CHECK(cudaSetDevice(device));
-  upload_tables(device);
   std::unique_ptr<Operator> op(new Operator);
   op->degree            = d.degree;
   op->number            = d.number;
   op->device            = device;
   op->geometry_type     = d.geometry_type;
   op->apply_constraints = d.apply_constraints;
-  if (const char *e = std::getenv("MFHN_TEXTURE")) op->use_texture = std::atoi(e);
   op->kernel            = d.kernel;
   op->n_cells           = d.n_cells;
   op->n_owned           = d.n_owned;
@@ -641,90 +307,9 @@ Operator *op_create(const mfhn_op_desc &d)
             if (d.segments[i] < d.segments[i - 1] || d.segments[i] > d.n_cells) throw InvalidArgument("segments must be ascending");
         }
       if (bulk_supported(n)) bulk_build(op->bulk, n, d.number, d.n_cells, nvec, d.dof_indices);
-      if (plane_supported(n) && (d.kernel == MFHN_KERNEL_PATCH || std::getenv("MFHN_BUILD_PATCH"))) op->patch.build(n, d.number, d.n_cells, d.dof_indices);
     }
   resolve_kernel(*op);
   return op.release();
-}
-
-// ---------------------------------------------------------------------------
-// auxiliary kernels
-template <typename Number>
-__global__ void pack_kernel(Number *buf, const Number *vec, const int32_t *idx, long long n)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) buf[i] = vec[idx[i]];
-}
-template <typename Number>
-__global__ void unpack_add_kernel(Number *vec, const Number *buf, const int32_t *idx, long long n)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) vec[idx[i]] += buf[i];
-}
-
-template <int n, typename Number>
-__global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n_cells, int transpose)
-{
-  // FEEvaluationHangingNodesFactory::apply on cell-local values (benchmark_00_likwid.cc:56-59)
-  __shared__ Number s[n * n * n];
-  const long long cell = blockIdx.x;
-  if (masks[cell] == 0) return; // unconstrained cell: nothing to interpolate (block-uniform)
-  const int l = threadIdx.x, a = l % n, b = l / n;
-  Number *g = values + cell * (n * n * n);
-  for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
-  unsigned face, edge, cb;
-  const unsigned mask = masks[cell];
-  decode_mask(mask, face, edge, cb);
-  __syncthreads();
-  for (int d = 0; d < 3; ++d)
-    {
-      Number *line   = s + (d == 0 ? n * (a + n * b) : d == 1 ? a + n * n * b : a + n * b);
-      const int strd = d == 0 ? 1 : d == 1 ? n : n * n;
-      if (mask)
-        {
-          if (transpose)
-            hn_pass_line<n, true>(line, strd, d, a, b, face, edge, cb);
-          else
-            hn_pass_line<n, false>(line, strd, d, a, b, face, edge, cb);
-        }
-      __syncthreads();
-    }
-  for (int z = 0; z < n; ++z) g[l + n * n * z] = s[l + n * n * z];
-}
-
-template <typename Number>
-void hn_only(Operator &op, void *values, int transpose, cudaStream_t st)
-{
-  if (op.n_cells == 0) return;
-  const unsigned grid = (unsigned)op.n_cells;
-#define HN_CASE(N)                                                                                            \
-  case N - 1:                                                                                                 \
-    hn_only_kernel<N, Number><<<grid, N * N, 0, st>>>((Number *)values, op.d_masks, op.n_cells, transpose); \
-    break;
-  switch (op.degree)
-    {
-      HN_CASE(2) HN_CASE(3) HN_CASE(4) HN_CASE(5) HN_CASE(6) HN_CASE(7) HN_CASE(8) HN_CASE(9)
-    }
-#undef HN_CASE
-  CUDA_CHECK(cudaGetLastError());
-  ++op.launches;
-}
-
-template <typename Number>
-__global__ void fma_bench_kernel(Number *out, int iters)
-{
-  Number a[8], x = Number(1.0) + Number(1e-9) * threadIdx.x, y = Number(0.5);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = Number(i) * Number(0.125) + x;
-  for (int it = 0; it < iters; ++it)
-    {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = a[i] * x + y;
-    }
-  Number s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += a[i];
-  if (s == Number(-1)) out[0] = s;
 }
 
 // ---------------------------------------------------------------------------
@@ -778,16 +363,11 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   const size_t s = op.number == MFHN_F64 ? 8 : 4;
   char *dstb = static_cast<char *>(dst);
   char *srcb = static_cast<char *>(const_cast<void *>(src));
-  const unsigned grid = (unsigned)((d.n_import + 255) / 256);
   if (zero_dst) CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)(op.n_owned + op.n_ghost) * s, main));
   // pack the entries the peers ghost
   if (d.n_import > 0)
     {
-      if (op.number == MFHN_F64)
-        pack_all_kernel<double><<<grid, 256, 0, main>>>((double *)d.d_send, (const double *)src, d.d_import_idx, d.n_import);
-      else
-        pack_all_kernel<float><<<grid, 256, 0, main>>>((float *)d.d_send, (const float *)src, d.d_import_idx, d.n_import);
-      CUDA_CHECK(cudaGetLastError());
+      run_pack(op.number, d.d_send, src, d.d_import_idx, d.n_import, main);
       ++d.launches;
     }
   CUDA_CHECK(cudaEventRecord(d.ev[0], main));
@@ -821,11 +401,7 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
   if (d.n_import > 0)
     {
-      if (op.number == MFHN_F64)
-        unpack_add_all_kernel<double><<<grid, 256, 0, main>>>((double *)dst, (const double *)d.d_recv, d.d_import_idx, d.n_import);
-      else
-        unpack_add_all_kernel<float><<<grid, 256, 0, main>>>((float *)dst, (const float *)d.d_recv, d.d_import_idx, d.n_import);
-      CUDA_CHECK(cudaGetLastError());
+      run_unpack_add(op.number, dst, d.d_recv, d.d_import_idx, d.n_import, true, main); // several peers may add to one entry
       ++d.launches;
     }
   if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(dstb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
@@ -835,7 +411,6 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
 // boundary cells read the owners' src entries and add into the owners' dst entries directly
 // over NVLink; a second barrier makes the remote contributions visible before anyone consumes
 // dst.  The barriers are 4-byte NCCL all-reduces.
-template <typename Number>
 void dist_vmult_peer_n(Dist &d, cudaStream_t main)
 {
   Operator &op = *d.op;
@@ -855,15 +430,8 @@ void dist_vmult_peer_n(Dist &d, cudaStream_t main)
     if (ce <= cb) return;
     p.cell_begin = cb;
     p.cell_end   = ce;
-    switch (op.degree)
-      {
-        case 1: launch_plane<2, Number>(op.plane, p, op.device, st, 0, peer); break;
-        case 2: launch_plane<3, Number>(op.plane, p, op.device, st, 0, peer); break;
-        case 3: launch_plane<4, Number>(op.plane, p, op.device, st, 0, peer); break;
-        case 4: launch_plane<5, Number>(op.plane, p, op.device, st, 0, peer); break;
-        case 5: launch_plane<6, Number>(op.plane, p, op.device, st, 0, peer); break;
-        default: throw NotImplemented("peer mode covers the register-tiled plane kernel (degree <= 5)");
-      }
+    if (op.degree > 5) throw NotImplemented("peer mode covers the register-tiled plane kernel (degree <= 5)");
+    run_plane(op.degree, op.number, op.plane, p, op.device, st, peer);
     ++op.launches;
     ++d.launches;
   };
@@ -956,10 +524,7 @@ int mfhn_op_diagonal(mfhn_op h, void *diag, void *stream)
     p.cell_begin        = 0;
     p.cell_end          = op.n_cells;
     p.apply_constraints = op.apply_constraints;
-    if (op.number == MFHN_F64)
-      launch_diagonal<double>(op, p, static_cast<cudaStream_t>(stream));
-    else
-      launch_diagonal<float>(op, p, static_cast<cudaStream_t>(stream));
+    launch_diagonal(op, p, static_cast<cudaStream_t>(stream));
   });
 }
 int mfhn_op_set_apply_constraints(mfhn_op h, int v)
@@ -994,10 +559,8 @@ int mfhn_op_apply_hn(mfhn_op h, void *values, int transpose, void *stream)
     if (!h || !values) throw InvalidArgument("null argument");
     Operator &op = *reinterpret_cast<Operator *>(h);
     CUDA_CHECK(cudaSetDevice(op.device));
-    if (op.number == MFHN_F64)
-      hn_only<double>(op, values, transpose, static_cast<cudaStream_t>(stream));
-    else
-      hn_only<float>(op, values, transpose, static_cast<cudaStream_t>(stream));
+    run_hn_only(op.degree, op.number, values, op.d_masks, op.n_cells, transpose, static_cast<cudaStream_t>(stream));
+    ++op.launches;
   });
 }
 int mfhn_op_query(mfhn_op h, const char *what, double *value)
@@ -1018,10 +581,6 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
       *value = 3 * s * nvec + (double)op.n_cells * (4 * n3 + 1 + (op.geometry_type == MFHN_GEOM_CARTESIAN ? 3 * s : op.geometry_type == MFHN_GEOM_AFFINE ? 10 * s : 6 * s * n3));
     else if (w == "algorithmic_flops") // even-odd sum factorisation count of SURVEY 8d, without HN terms
       *value = (double)op.n_cells * (12 * n * n * (n * n + 2 * n) + 3 * n3);
-    else if (w == "unique_dofs_per_cell")
-      *value = op.patch.unique_per_cell;
-    else if (w == "patch_index_bytes")
-      *value = (double)op.patch.index_bytes;
     else if (w == "kernel")
       *value = (double)resolve_kernel(op);
     else if (w == "bulk_irregular_cells") // cells the bulk-copy kernel leaves to the plane kernel (-1: layout not usable)
@@ -1047,62 +606,17 @@ int mfhn_bulk_layout_check(int degree, int number, int64_t n_cells, int64_t n_ve
 
 int mfhn_pack(int number, void *buffer, const void *vec, const int32_t *idx, int64_t n, void *stream)
 {
-  return guard([&] {
-    if (n <= 0) return;
-    const unsigned grid = (unsigned)((n + 255) / 256);
-    cudaStream_t st     = static_cast<cudaStream_t>(stream);
-    if (number == MFHN_F64)
-      pack_kernel<double><<<grid, 256, 0, st>>>((double *)buffer, (const double *)vec, idx, n);
-    else
-      pack_kernel<float><<<grid, 256, 0, st>>>((float *)buffer, (const float *)vec, idx, n);
-    CUDA_CHECK(cudaGetLastError());
-  });
+  return guard([&] { run_pack(number, buffer, vec, idx, n, static_cast<cudaStream_t>(stream)); });
 }
 int mfhn_unpack_add(int number, void *vec, const void *buffer, const int32_t *idx, int64_t n, void *stream)
 {
-  return guard([&] {
-    if (n <= 0) return;
-    const unsigned grid = (unsigned)((n + 255) / 256);
-    cudaStream_t st     = static_cast<cudaStream_t>(stream);
-    if (number == MFHN_F64)
-      unpack_add_kernel<double><<<grid, 256, 0, st>>>((double *)vec, (const double *)buffer, idx, n);
-    else
-      unpack_add_kernel<float><<<grid, 256, 0, st>>>((float *)vec, (const float *)buffer, idx, n);
-    CUDA_CHECK(cudaGetLastError());
-  });
+  return guard([&] { run_unpack_add(number, vec, buffer, idx, n, false, static_cast<cudaStream_t>(stream)); });
 }
 int mfhn_bench_dfma(int number, int iters, double *tflops)
 {
   return guard([&] {
     if (!tflops) throw InvalidArgument("null argument");
-    void *out = nullptr;
-    CUDA_CHECK(cudaMalloc(&out, 64));
-    cudaDeviceProp prop;
-    int dev;
-    CUDA_CHECK(cudaGetDevice(&dev));
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256;
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0));
-    CUDA_CHECK(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep)
-      {
-        CUDA_CHECK(cudaEventRecord(e0));
-        if (number == MFHN_F64)
-          fma_bench_kernel<double><<<blocks, threads>>>((double *)out, iters);
-        else
-          fma_bench_kernel<float><<<blocks, threads>>>((float *)out, iters);
-        CUDA_CHECK(cudaEventRecord(e1));
-        CUDA_CHECK(cudaEventSynchronize(e1));
-        float ms;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best) best = ms;
-      }
-    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(out);
+    *tflops = run_fma_bench(number, iters);
   });
 }
 
@@ -1246,10 +760,7 @@ int mfhn_dist_vmult_peer(mfhn_dist h, void *stream, int zero_dst)
     CUDA_CHECK(cudaSetDevice(op.device));
     cudaStream_t main = static_cast<cudaStream_t>(stream);
     if (zero_dst) CUDA_CHECK(cudaMemsetAsync(d.peer_dst_local, 0, (size_t)(op.n_owned + op.n_ghost) * (op.number == MFHN_F64 ? 8 : 4), main));
-    if (op.number == MFHN_F64)
-      dist_vmult_peer_n<double>(d, main);
-    else
-      dist_vmult_peer_n<float>(d, main);
+    dist_vmult_peer_n(d, main);
   });
 }
 }

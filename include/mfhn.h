@@ -51,7 +51,7 @@ typedef struct mfhn_op_s *mfhn_op;
 #define MFHN_KERNEL_SEPARABLE 2 /* Cartesian cells only: 1D mass/stiffness tensor form        */
 #define MFHN_KERNEL_BASELINE 3  /* restatement of the deal.II CUDA design (one thread per DoF) */
 #define MFHN_KERNEL_PLANE 4     /* Cartesian cells, register-tiled separable kernel, per-cell gather */
-#define MFHN_KERNEL_PATCH 5     /* same arithmetic, patch-wise sorted-unique gather/scatter (experimental) */
+#define MFHN_KERNEL_PATCH 5     /* removed (round-1 experiment: sorted-unique patch gather, slower than PLANE); returns MFHN_ERR_NOT_IMPL */
 #define MFHN_KERNEL_BULK 6      /* plane kernel; cell-interior and face blocks moved by the bulk-copy engine
                                    (cp.async.bulk / cp.reduce.async.bulk), degrees 3..5, 16-byte aligned vectors */
 

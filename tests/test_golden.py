@@ -50,7 +50,7 @@ def test_cpp_setup_reproduces_golden_bit_exact(path, mfhn):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", FIXTURES, ids=os.path.basename)
-@pytest.mark.parametrize("kernel", ["auto", "qpoint", "separable", "plane", "bulk", "patch", "baseline"])
+@pytest.mark.parametrize("kernel", ["auto", "qpoint", "separable", "plane", "bulk", "baseline"])
 def test_cuda_reproduces_golden(path, kernel, mfhn):
     import torch
 

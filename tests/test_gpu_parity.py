@@ -44,15 +44,13 @@ def _run(mfhn, mf, x, number, kernel, apply_constraints=True):
     return dst.cpu().numpy().astype(np.float64), op
 
 
-KERNELS = ["qpoint", "separable", "plane", "bulk", "patch", "baseline"]
+KERNELS = ["qpoint", "separable", "plane", "bulk", "baseline"]
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("number", ["double", "float"])
 def test_vmult_matches_oracle_annulus(mfhn, k, kernel, number):
-    if kernel == "patch" and k > 5:
-        pytest.skip("the patch kernel covers degree <= 5")
     if kernel == "bulk" and not 3 <= k <= 5:
         pytest.skip("the bulk-copy kernel covers degrees 3..5")
     L = 5 if k <= 4 else 4 if k <= 6 else 3
@@ -228,7 +226,7 @@ def test_error_behaviour(mfhn):
     dh = mfhn.DoFHandler(tria, 6)
     mf = mfhn.MatrixFree(dh)
     with pytest.raises(mfhn.MfhnError):
-        mfhn.LaplaceOperator(mf, kernel="patch")  # not available for this degree
+        mfhn.LaplaceOperator(mf, kernel="bulk")  # not available for this degree
     op = mfhn.LaplaceOperator(mf)
     v = op.initialize_dof_vector()
     with pytest.raises(mfhn.MfhnError):
