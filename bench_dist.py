@@ -118,7 +118,7 @@ def stage_benchmarks(mfhn, torch, args, L, time_vmult):
     dg.degree, dg.n_cells, dg.h, dg.masks = mf.degree, mf.n_cells, mf.h, mf.masks
     dg.dof_indices = np.arange(mf.n_cells * n3, dtype=np.uint32).reshape(mf.n_cells, n3)
     dg.n_interior_cells = dg.n_interior_a = mf.n_cells
-    dg.partitioner = mfhn.Partitioner(0, 1, (0, mf.n_cells * n3), np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64))
+    dg.partitioner = mfhn.Partitioner(owned_range=(0, mf.n_cells * n3))
     op = mfhn.LaplaceOperator(dg, number=args.number)
     src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
     src.fill_(1.0)

@@ -13,8 +13,8 @@ operator interface.  Importing fails loudly if the library has not been built.
 from . import _capi as capi
 from ._capi import MfhnError, NotImplementedMfhn
 from .api import (DoFHandler, LaplaceOperator, MatrixFree, Partitioner, Triangulation, bench_fma,
-                  exchange_import_indices)
+                  exchange_import_indices, exchange_local)
 from .solvers import solve_cg
 
 __all__ = ["capi", "MfhnError", "NotImplementedMfhn", "Triangulation", "DoFHandler", "MatrixFree",
-           "Partitioner", "LaplaceOperator", "bench_fma", "exchange_import_indices", "solve_cg"]
+           "Partitioner", "LaplaceOperator", "bench_fma", "exchange_import_indices", "exchange_local", "solve_cg"]

@@ -42,6 +42,16 @@ class OpDesc(C.Structure):
     ]
 
 
+class MfOptions(C.Structure):
+    _fields_ = [("rank", c_int), ("categorize", c_int), ("window", c_int), ("batch_alignment", c_int)]
+
+
+class MfSizes(C.Structure):
+    _fields_ = [("degree", c_int), ("rank", c_int), ("n_ranks", c_int), ("n_cells", c_int64), ("n_cells_hn", c_int64),
+                ("n_owned", c_int64), ("n_ghost", c_int64), ("owned_begin", c_int64), ("n_interior_a", c_int64),
+                ("n_interior", c_int64), ("n_ghost_peers", c_int), ("n_import_peers", c_int), ("n_import", c_int64)]
+
+
 class DistDesc(C.Structure):
     _fields_ = [
         ("rank", c_int),
@@ -79,10 +89,18 @@ SIGNATURES = {
     "mfhn_dofs_cells_of_rank": (c_int, [c_void_p, c_int, c_void_p]),
     "mfhn_dofs_fill": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mfhn_dofs_support_points": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
+    "mfhn_mf_create": (c_int, [c_void_p, P(MfOptions), P(c_void_p)]),
+    "mfhn_mf_destroy": (None, [c_void_p]),
+    "mfhn_mf_info": (c_int, [c_void_p, P(MfSizes)]),
+    "mfhn_mf_arrays": (c_int, [c_void_p] + [P(c_void_p)] * 6),
+    "mfhn_mf_partitioner": (c_int, [c_void_p] + [P(c_void_p)] * 7),
+    "mfhn_mf_set_imports": (c_int, [c_void_p, c_int, c_void_p, c_int64]),
+    "mfhn_mf_exchange_local": (c_int, [P(c_void_p), c_int]),
     "mfhn_compress": (C.c_uint8, [C.c_uint16]),
     "mfhn_decompress": (C.c_uint16, [C.c_uint8]),
     "mfhn_check_kind": (c_int, [C.c_uint16]),
     "mfhn_op_create": (c_int, [P(OpDesc), P(c_void_p)]),
+    "mfhn_op_create_mf": (c_int, [c_void_p, c_int, c_int, c_int, c_int, P(c_void_p)]),
     "mfhn_op_destroy": (None, [c_void_p]),
     "mfhn_op_vmult": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "mfhn_op_vmult_range": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64]),
@@ -100,6 +118,7 @@ SIGNATURES = {
     "mfhn_bulk_layout_check": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, P(c_int64), P(c_int64)]),
     "mfhn_dist_unique_id": (c_int, [c_void_p]),
     "mfhn_dist_create": (c_int, [c_void_p, P(DistDesc), P(c_void_p)]),
+    "mfhn_dist_create_mf": (c_int, [c_void_p, c_void_p, c_void_p, P(c_void_p)]),
     "mfhn_dist_destroy": (None, [c_void_p]),
     "mfhn_dist_vmult": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "mfhn_dist_launch_count": (c_int64, [c_void_p]),

@@ -124,25 +124,50 @@ class DoFHandler:
         return out
 
 
-class Partitioner:
-    """Utilities::MPI::Partitioner analogue: owned range, sorted ghost indices,
-    per-peer ghost ranges and import index lists."""
+def _view(ptr, n, dtype):
+    """numpy view of n entries of a host array owned by a C handle (empty array for n == 0)."""
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    ct = np.ctypeslib.as_ctypes_type(dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(int(n),))
 
-    def __init__(self, rank, n_ranks, owned_range, ghost_global, rank_begin):
-        self.rank, self.n_ranks = rank, n_ranks
-        self.begin, self.end = owned_range
-        self.n_owned = self.end - self.begin
-        self.ghost_global = ghost_global
-        self.n_ghost = len(ghost_global)
-        self.rank_begin = np.asarray(rank_begin, dtype=np.int64)
-        owner = np.searchsorted(rank_begin, ghost_global, side="right") - 1
-        self.ghost_owner = owner.astype(np.int32)
-        # ghosts are sorted by global index, owners' ranges are ascending => contiguous per peer
-        self.ghost_ranges = {}
-        for p in np.unique(owner):
-            w = np.nonzero(owner == p)[0]
-            self.ghost_ranges[int(p)] = (int(w[0]), int(w[-1]) + 1)
-        self.import_indices = {}  # peer -> local owned indices the peer reads (set by exchange)
+
+class Partitioner:
+    """Utilities::MPI::Partitioner analogue: owned range, sorted ghost indices, per-peer ghost ranges and
+    import index lists.  A view of the data held by the MatrixFree handle (mfhn_mf_partitioner)."""
+
+    def __init__(self, mf_handle=None, keep=None, rank=0, n_ranks=1, owned_range=(0, 0)):
+        self._mf, self._keep = mf_handle, keep  # keep: the object that owns the handle
+        if mf_handle is None:  # a serial stand-in (no ghosts): used by synthetic layouts in the benchmarks
+            self.rank, self.n_ranks = rank, n_ranks
+            self.begin, self.end = owned_range
+            self.n_owned, self.n_ghost = self.end - self.begin, 0
+            self.ghost_global, self.ghost_owner = np.zeros(0, np.int64), np.zeros(0, np.int32)
+            self.rank_begin = np.array([self.begin, self.end], dtype=np.int64)
+            self.ghost_ranges, self.import_indices = {}, {}
+            return
+        self._refresh()
+
+    def _refresh(self):
+        sz = capi.MfSizes()
+        check(lib.mfhn_mf_info(self._mf, C.byref(sz)))
+        self.rank, self.n_ranks = sz.rank, sz.n_ranks
+        self.begin, self.end = sz.owned_begin, sz.owned_begin + sz.n_owned
+        self.n_owned, self.n_ghost = sz.n_owned, sz.n_ghost
+        p = [C.c_void_p() for _ in range(6)]
+        check(lib.mfhn_mf_arrays(self._mf, *[C.byref(x) for x in p]))
+        self.ghost_global = _view(p[4], sz.n_ghost, np.int64)
+        self.ghost_owner = _view(p[5], sz.n_ghost, np.int32)
+        q = [C.c_void_p() for _ in range(7)]
+        check(lib.mfhn_mf_partitioner(self._mf, *[C.byref(x) for x in q]))
+        gp = _view(q[0], sz.n_ghost_peers, np.int32)
+        gb, ge = _view(q[1], sz.n_ghost_peers, np.int64), _view(q[2], sz.n_ghost_peers, np.int64)
+        self.ghost_ranges = {int(gp[i]): (int(gb[i]), int(ge[i])) for i in range(sz.n_ghost_peers)}
+        ip = _view(q[3], sz.n_import_peers, np.int32)
+        io = _view(q[4], sz.n_import_peers + 1, np.int64)
+        ii = _view(q[5], sz.n_import, np.int32)
+        self.import_indices = {int(ip[i]): ii[io[i]:io[i + 1]] for i in range(sz.n_import_peers)}
+        self.rank_begin = _view(q[6], sz.n_ranks + 1, np.int64)
 
     def n_ghost_indices(self):
         return self.n_ghost
@@ -156,67 +181,59 @@ class Partitioner:
 
     def set_imports(self, requests_from_peers):
         """requests_from_peers: peer -> global indices (owned here) that the peer ghosts."""
-        self.import_indices = {int(p): (np.asarray(g, dtype=np.int64) - self.begin).astype(np.int32) for p, g in requests_from_peers.items() if len(g)}
-        for v in self.import_indices.values():
-            assert v.min() >= 0 and v.max() < self.n_owned
+        for p, g in requests_from_peers.items():
+            g = np.ascontiguousarray(g, dtype=np.int64)
+            check(lib.mfhn_mf_set_imports(self._mf, int(p), _ptr(g), len(g)))
+        self._refresh()
 
 
 class MatrixFree:
-    """Rank-local setup product of MatrixFree::reinit (benchmark_03.h:338-339):
-    cell order (Morton, interior cells first), rank-local substituted DoF
-    indices, compressed masks, Cartesian geometry and the ghost partitioner."""
+    """Rank-local setup product of MatrixFree::reinit (benchmark_03.h:338-339), computed by the library
+    (mfhn_mf_create): cell order (Morton, interior cells first, categorised by constraint mask like the reference's
+    Categorize option, benchmark_01.h:258-284), rank-local substituted DoF indices, compressed masks, Cartesian
+    geometry and the ghost partitioner.  The numpy attributes are views of the handle's host arrays."""
 
     def __init__(self, dof_handler: DoFHandler, rank: int = 0, categorize: bool = True):
         self.dof_handler, self.rank = dof_handler, rank
-        dh = dof_handler
-        self.degree = dh.degree
-        cells = dh.cells_of_rank(rank)
-        pos = dh.tria.morton_position()
-        cells = cells[np.argsort(pos[cells], kind="stable")]
-        _, sub, masks, h = dh.fill(cells)
-        b, e = dh.owned_range(rank)
-        rank_begin = np.array([dh.owned_range(r)[0] for r in range(dh.n_ranks)], dtype=np.int64)
-        flat = sub.reshape(-1).astype(np.int64)
-        is_ghost = (flat < b) | (flat >= e)
-        ghost_global = np.unique(flat[is_ghost])
-        local = flat - b
-        if len(ghost_global):
-            local[is_ghost] = (e - b) + np.searchsorted(ghost_global, flat[is_ghost])
-        assert local.max(initial=0) < 2 ** 32
-        local = local.reshape(sub.shape)
-        # cells touching ghost entries go last: [interior | boundary]
-        touches = is_ghost.reshape(sub.shape).any(axis=1)
-        order = np.concatenate([np.nonzero(~touches)[0], np.nonzero(touches)[0]])
-        self.n_interior_cells = int((~touches).sum())
-        if dh.n_ranks > 1:
-            # partition boundaries on whole warp batches of the cell kernels (16, 10, 8, 6, 5, 4 cells per warp for
-            # k = 1..6; lcm 240): the last few interior cells simply join the boundary partition
-            self.n_interior_cells -= self.n_interior_cells % 240
-        if categorize:
-            # the reference's Categorize option (benchmark_01.h:258-284: cell_vectorization_category =
-            # constraint mask): inside windows of the Morton order, cells are grouped by their constraint
-            # mask, so that fewer warps pay for the interpolation and a warp holds few different
-            # constraint kinds (= few different interpolation passes); locality is kept at window scale.
-            # Measured on B200 (k=4 / k=5): window 240 by flag 84.3 / 82.0, by kind 86.1 / 89.4,
-            # window 960 by kind 86.9 / 93.0, window 3840 by kind 87.2 / 93.8 GDoF/s (plane kernel); bulk-copy
-            # kernel at k=4: 960: 95.1, 3840: 95.7, 15360: 93.5.
-            w = int(os.environ.get("MFHN_CATEGORIZE_WINDOW", "3840"))
-            key = masks[order].astype(np.int64) if os.environ.get("MFHN_CATEGORIZE_BY_KIND", "1") == "1" else (masks[order] != 0).astype(np.int64)
-            seg = (np.arange(len(order)) >= self.n_interior_cells).astype(np.int64)
-            pos = np.arange(len(order))
-            window = np.where(seg == 0, pos, pos - self.n_interior_cells) // w
-            order = order[np.lexsort((pos, key, window, seg))]
-        # deal.II's cell_loop overlaps the two ghost exchanges with two interior partitions
-        self.n_interior_a = (self.n_interior_cells // 2) // 240 * 240 if dh.n_ranks > 1 else self.n_interior_cells
-        self.cell_ids = cells[order]
-        self.dof_indices = np.ascontiguousarray(local[order].astype(np.uint32))
-        self.masks = np.ascontiguousarray(masks[order])
-        self.h = np.ascontiguousarray(h[order])
-        self.n_cells = len(cells)
-        self.partitioner = Partitioner(rank, dh.n_ranks, (b, e), ghost_global, rank_begin)
+        self.degree = dof_handler.degree
+        # development switches: window size and grouping key of the categorisation.  Measured on B200 (k=4 / k=5):
+        # window 240 by flag 84.3 / 82.0, by kind 86.1 / 89.4, window 960 by kind 86.9 / 93.0, window 3840 by kind
+        # 87.2 / 93.8 GDoF/s (plane kernel); bulk-copy kernel at k=4: 960: 95.1, 3840: 95.7, 15360: 93.5.
+        by_kind = os.environ.get("MFHN_CATEGORIZE_BY_KIND", "1") == "1"
+        opt = capi.MfOptions(rank=rank, categorize=(1 if by_kind else 2) if categorize else 0,
+                             window=int(os.environ.get("MFHN_CATEGORIZE_WINDOW", "0")), batch_alignment=0)
+        h = C.c_void_p()
+        check(lib.mfhn_mf_create(dof_handler._h, C.byref(opt), C.byref(h)))
+        self._h = h
+        sz = capi.MfSizes()
+        check(lib.mfhn_mf_info(h, C.byref(sz)))
+        self.n_cells, self.n_interior_cells, self.n_interior_a = sz.n_cells, sz.n_interior, sz.n_interior_a
+        self._n_cells_hn = sz.n_cells_hn
+        p = [C.c_void_p() for _ in range(6)]
+        check(lib.mfhn_mf_arrays(h, *[C.byref(x) for x in p]))
+        n3 = (self.degree + 1) ** 3
+        self.cell_ids = _view(p[0], sz.n_cells, np.int64)
+        self.dof_indices = _view(p[1], sz.n_cells * n3, np.uint32).reshape(sz.n_cells, n3)
+        self.masks = _view(p[2], sz.n_cells, np.uint8)
+        self.h = _view(p[3], sz.n_cells, np.float64)
+        self.partitioner = Partitioner(h)  # a view: valid as long as this object lives
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.mfhn_mf_destroy(self._h)
+            self._h = None
 
     def n_cells_hn(self):
-        return int((self.masks != 0).sum())
+        return int(self._n_cells_hn)
+
+
+def exchange_local(matrix_frees):
+    """Import lists of all ranks when every rank's MatrixFree lives in this process (tests, one process driving
+    several devices): mfhn_mf_exchange_local."""
+    arr = (C.c_void_p * len(matrix_frees))(*[mf._h for mf in matrix_frees])
+    check(lib.mfhn_mf_exchange_local(arr, len(matrix_frees)))
+    for mf in matrix_frees:
+        mf.partitioner._refresh()
 
 
 def exchange_import_indices(partitioner: Partitioner, group=None):

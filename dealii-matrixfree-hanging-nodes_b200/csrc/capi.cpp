@@ -2,6 +2,7 @@
 #include "../../include/mfhn.h"
 #include "dof_handler.hpp"
 #include "error.hpp"
+#include "matrix_free.hpp"
 #include "octree.hpp"
 
 #include <memory>
@@ -104,7 +105,8 @@ int mfhn_mesh_partition(mfhn_mesh m, int n_ranks, double hn_weight, int32_t *ran
     double total = 0;
     for (size_t p = 0; p < order.size(); ++p)
       {
-        w[p] = kinds[order[p]] != 0 ? 1.0 + 10.0 * hn_weight : 11.0;
+        // (the reference's weight callback returns unsigned int: 1 + 10 w is truncated, benchmark_02.cc:19-33)
+        w[p] = kinds[order[p]] != 0 ? (double)(unsigned)(1.0 + 10.0 * hn_weight) : 11.0;
         total += w[p];
       }
     double prefix = 0;
@@ -196,6 +198,105 @@ int mfhn_dofs_support_points(mfhn_dofs d, int64_t begin, int64_t end, double *xy
     dh.support_points(begin, end, xyz);
   });
 }
+
+// ---- MatrixFree::reinit ---------------------------------------------------------------------
+int mfhn_mf_create(mfhn_dofs d, const mfhn_mf_options *options, mfhn_mf *out)
+{
+  return guard([&] {
+    if (!d || !out) throw InvalidArgument("null argument");
+    DofsHandle &dh = *reinterpret_cast<DofsHandle *>(d);
+    MatrixFreeOptions opt;
+    if (options)
+      {
+        opt.rank       = options->rank;
+        opt.categorize = options->categorize;
+        if (options->window > 0) opt.window = options->window;
+        if (options->batch_alignment > 0) opt.batch_alignment = options->batch_alignment;
+      }
+    if (opt.categorize < 0 || opt.categorize > 2) throw InvalidArgument("categorize must be 0, 1 or 2");
+    std::unique_ptr<MatrixFreeData> mf(new MatrixFreeData);
+    mf->reinit(dh.dh, dh.mesh->tree, opt);
+    *out = reinterpret_cast<mfhn_mf>(mf.release());
+  });
+}
+void mfhn_mf_destroy(mfhn_mf m) { delete reinterpret_cast<MatrixFreeData *>(m); }
+int mfhn_mf_info(mfhn_mf m, mfhn_mf_sizes *out)
+{
+  return guard([&] {
+    if (!m || !out) throw InvalidArgument("null argument");
+    const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(m);
+    out->degree         = mf.degree;
+    out->rank           = mf.rank;
+    out->n_ranks        = mf.n_ranks;
+    out->n_cells        = mf.n_cells;
+    out->n_cells_hn     = mf.n_cells_hn();
+    out->n_owned        = mf.n_owned;
+    out->n_ghost        = mf.n_ghost;
+    out->owned_begin    = mf.owned_begin;
+    out->n_interior_a   = mf.n_interior_a;
+    out->n_interior     = mf.n_interior;
+    out->n_ghost_peers  = (int)mf.ghost_peers.size();
+    out->n_import_peers = (int)mf.import_peers.size();
+    out->n_import       = (int64_t)mf.import_indices.size();
+  });
+}
+int mfhn_mf_arrays(mfhn_mf m, const int64_t **cell_ids, const uint32_t **dof_indices, const uint8_t **masks, const double **h,
+                   const int64_t **ghost_global, const int32_t **ghost_owner)
+{
+  return guard([&] {
+    if (!m) throw InvalidArgument("null argument");
+    const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(m);
+    if (cell_ids) *cell_ids = mf.cell_ids.data();
+    if (dof_indices) *dof_indices = mf.dof_indices.data();
+    if (masks) *masks = mf.masks.data();
+    if (h) *h = mf.h.data();
+    if (ghost_global) *ghost_global = mf.ghost_global.data();
+    if (ghost_owner) *ghost_owner = mf.ghost_owner.data();
+  });
+}
+int mfhn_mf_partitioner(mfhn_mf m, const int32_t **ghost_peers, const int64_t **ghost_begin, const int64_t **ghost_end,
+                        const int32_t **import_peers, const int64_t **import_offsets, const int32_t **import_indices, const int64_t **rank_begin)
+{
+  return guard([&] {
+    if (!m) throw InvalidArgument("null argument");
+    const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(m);
+    if (ghost_peers) *ghost_peers = mf.ghost_peers.data();
+    if (ghost_begin) *ghost_begin = mf.ghost_begin.data();
+    if (ghost_end) *ghost_end = mf.ghost_end.data();
+    if (import_peers) *import_peers = mf.import_peers.data();
+    if (import_offsets) *import_offsets = mf.import_offsets.data();
+    if (import_indices) *import_indices = mf.import_indices.data();
+    if (rank_begin) *rank_begin = mf.rank_begin.data();
+  });
+}
+int mfhn_mf_set_imports(mfhn_mf m, int peer, const int64_t *global_indices, int64_t n)
+{
+  return guard([&] {
+    if (!m || (n > 0 && !global_indices)) throw InvalidArgument("null argument");
+    reinterpret_cast<MatrixFreeData *>(m)->set_imports(peer, global_indices, n);
+  });
+}
+int mfhn_mf_exchange_local(mfhn_mf *all, int n_ranks)
+{
+  return guard([&] {
+    if (!all) throw InvalidArgument("null argument");
+    for (int r = 0; r < n_ranks; ++r)
+      {
+        if (!all[r]) throw InvalidArgument("null argument");
+        const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(all[r]);
+        if (mf.rank != r || mf.n_ranks != n_ranks) throw InvalidArgument("handles must be ordered by rank");
+      }
+    // what rank r ghosts from owner o is what o imports for r
+    for (int r = 0; r < n_ranks; ++r)
+      {
+        const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(all[r]);
+        for (size_t p = 0; p < mf.ghost_peers.size(); ++p)
+          reinterpret_cast<MatrixFreeData *>(all[mf.ghost_peers[p]])
+            ->set_imports(r, mf.ghost_global.data() + mf.ghost_begin[p], mf.ghost_end[p] - mf.ghost_begin[p]);
+      }
+  });
+}
+
 uint8_t mfhn_compress(uint16_t kind) { return compress_kind(kind); }
 uint16_t mfhn_decompress(uint8_t c) { return decompress_kind(c); }
 int mfhn_check_kind(uint16_t kind) { return check_kind(kind) ? 1 : 0; }

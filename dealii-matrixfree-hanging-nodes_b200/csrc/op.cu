@@ -5,6 +5,7 @@
 #include "error.hpp"
 #include "fe1d.hpp"
 #include "layouts.hpp"
+#include "matrix_free.hpp"
 #include "dist.cuh"
 #include "octree.hpp"
 
@@ -459,6 +460,33 @@ int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out)
     *out = reinterpret_cast<mfhn_op>(op_create(*desc));
   });
 }
+int mfhn_op_create_mf(mfhn_mf m, int number, int kernel, int apply_constraints, int device, mfhn_op *out)
+{
+  return guard([&] {
+    if (!m || !out) throw InvalidArgument("null argument");
+    const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(m);
+    std::vector<int64_t> seg;
+    for (int64_t s : {(int64_t)0, mf.n_interior_a, mf.n_interior})
+      if (s < mf.n_cells && (seg.empty() || s > seg.back())) seg.push_back(s);
+    if (seg.empty()) seg.push_back(0);
+    mfhn_op_desc d{};
+    d.degree            = mf.degree;
+    d.number            = number;
+    d.n_cells           = mf.n_cells;
+    d.n_owned           = mf.n_owned;
+    d.n_ghost           = mf.n_ghost;
+    d.dof_indices       = mf.dof_indices.data();
+    d.masks             = mf.masks.data();
+    d.geometry_type     = MFHN_GEOM_CARTESIAN;
+    d.geometry          = mf.h.data();
+    d.apply_constraints = apply_constraints;
+    d.kernel            = kernel;
+    d.device            = device;
+    d.segments          = seg.data();
+    d.n_segments        = (int)seg.size();
+    *out                = reinterpret_cast<mfhn_op>(op_create(d));
+  });
+}
 void mfhn_op_destroy(mfhn_op op) { delete reinterpret_cast<Operator *>(op); }
 
 int mfhn_op_vmult(mfhn_op h, void *dst, const void *src, void *stream, int zero_dst)
@@ -671,6 +699,32 @@ int mfhn_dist_create(mfhn_op h, const mfhn_dist_desc *dd, mfhn_dist *out)
     NCCL_CHECK(nccl.CommInitRank(&d->comm, dd->world, id, dd->rank));
     *out = reinterpret_cast<mfhn_dist>(d.release());
   });
+}
+int mfhn_dist_create_mf(mfhn_op h, mfhn_mf m, const void *unique_id, mfhn_dist *out)
+{
+  if (!m)
+    {
+      set_last_error("null argument");
+      return MFHN_ERR_INVALID;
+    }
+  const MatrixFreeData &mf = *reinterpret_cast<MatrixFreeData *>(m);
+  mfhn_dist_desc dd{};
+  dd.rank           = mf.rank;
+  dd.world          = mf.n_ranks;
+  dd.unique_id      = unique_id;
+  dd.n_import_peers = (int)mf.import_peers.size();
+  dd.import_peers   = mf.import_peers.data();
+  dd.import_offsets = mf.import_offsets.data();
+  dd.import_indices = mf.import_indices.data();
+  dd.n_ghost_peers  = (int)mf.ghost_peers.size();
+  dd.ghost_peers    = mf.ghost_peers.data();
+  dd.ghost_begin    = mf.ghost_begin.data();
+  dd.ghost_end      = mf.ghost_end.data();
+  dd.segments[0]    = 0;
+  dd.segments[1]    = mf.n_interior_a;
+  dd.segments[2]    = mf.n_interior;
+  dd.segments[3]    = mf.n_cells;
+  return mfhn_dist_create(h, &dd, out);
 }
 void mfhn_dist_destroy(mfhn_dist d) { delete reinterpret_cast<Dist *>(d); }
 int mfhn_dist_vmult(mfhn_dist h, void *dst, const void *src, void *stream, int zero_dst)

@@ -109,6 +109,50 @@ int mfhn_dofs_fill(mfhn_dofs d, int64_t n, const int64_t *cell_ids, uint64_t *ra
  * VectorTools::interpolate needs (benchmark_03.h:459-461). */
 int mfhn_dofs_support_points(mfhn_dofs d, int64_t begin, int64_t end, double *xyz);
 
+/* ---------------------------------------------------------------------------
+ * MatrixFree::reinit (benchmark_03.h:326-340; benchmark_01.h:251-284 with the
+ * cell_vectorization_category of the Categorize option): the rank-local setup
+ * product -- loop order of the cells (Morton curve, interior cells first,
+ * grouped by constraint mask inside windows), rank-local DoF numbering (owned
+ * range, then ghosts sorted by global index), compressed masks, cell sizes and
+ * the Utilities::MPI::Partitioner data.  Host memory; the arrays returned by
+ * mfhn_mf_arrays / mfhn_mf_partitioner belong to the handle.
+ * ------------------------------------------------------------------------ */
+typedef struct mfhn_mf_s *mfhn_mf;
+typedef struct
+{
+  int rank;            /* rank whose cells are set up (0 for a serial DoF handler)                     */
+  int categorize;      /* 0: Morton order, 1: group by constraint mask, 2: by constrained/unconstrained  */
+  int window;          /* cells per categorisation window, 0 = default (3840)                          */
+  int batch_alignment; /* partition boundaries on multiples of this many cells, 0 = default (240)      */
+} mfhn_mf_options;
+typedef struct
+{
+  int degree, rank, n_ranks;
+  int64_t n_cells, n_cells_hn;
+  int64_t n_owned, n_ghost, owned_begin;
+  int64_t n_interior_a, n_interior; /* cells [0,a) | [a,interior) | [interior,n_cells) touch ghost entries   */
+  int n_ghost_peers, n_import_peers;
+  int64_t n_import;
+} mfhn_mf_sizes;
+int mfhn_mf_create(mfhn_dofs d, const mfhn_mf_options *options /* NULL = defaults */, mfhn_mf *out);
+void mfhn_mf_destroy(mfhn_mf m);
+int mfhn_mf_info(mfhn_mf m, mfhn_mf_sizes *out);
+/* cell_ids int64[n_cells] (storage indices in loop order), dof_indices uint32[n_cells*(k+1)^3], masks uint8[n_cells],
+ * h double[n_cells], ghost_global int64[n_ghost] (ascending), ghost_owner int32[n_ghost].  Any pointer may be NULL. */
+int mfhn_mf_arrays(mfhn_mf m, const int64_t **cell_ids, const uint32_t **dof_indices, const uint8_t **masks, const double **h,
+                   const int64_t **ghost_global, const int32_t **ghost_owner);
+/* Partitioner: per ghost peer its contiguous range inside the ghost section; per import peer the local owned indices it
+ * reads (import_offsets has n_import_peers + 1 entries); rank_begin[n_ranks + 1] = owned ranges of all ranks. */
+int mfhn_mf_partitioner(mfhn_mf m, const int32_t **ghost_peers, const int64_t **ghost_begin, const int64_t **ghost_end,
+                        const int32_t **import_peers, const int64_t **import_offsets, const int32_t **import_indices,
+                        const int64_t **rank_begin);
+/* The import lists come from the peers: rank `peer` ghosts the given global indices (all owned here).  Between processes the
+ * caller moves the requests (ghost_global ranges) with whatever transport it has; inside one process
+ * mfhn_mf_exchange_local does it for the handles of all ranks (ordered by rank). */
+int mfhn_mf_set_imports(mfhn_mf m, int peer, const int64_t *global_indices, int64_t n);
+int mfhn_mf_exchange_local(mfhn_mf *all_ranks, int n_ranks);
+
 /* ConstraintKinds <-> compressed byte (deal.II hanging_nodes_internal.h,
  * used at benchmark_00_likwid.cc:45-48). */
 uint8_t mfhn_compress(uint16_t kind);
@@ -141,6 +185,9 @@ typedef struct
 } mfhn_op_desc;
 
 int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out);
+/* The operator of a MatrixFree handle (Cartesian cells, segments = its three cell partitions): what
+ * LaplaceOperator's constructor does with matrix_free.reinit (benchmark_03.h:326-340). */
+int mfhn_op_create_mf(mfhn_mf m, int number, int kernel, int apply_constraints, int device, mfhn_op *out);
 void mfhn_op_destroy(mfhn_op op);
 
 /* dst (+)= A src on device vectors of n_owned+n_ghost entries of the operator's
@@ -223,6 +270,8 @@ typedef struct
 } mfhn_dist_desc;
 int mfhn_dist_unique_id(void *id128);
 int mfhn_dist_create(mfhn_op op, const mfhn_dist_desc *desc, mfhn_dist *out);
+/* Same from a MatrixFree handle whose import lists are set. */
+int mfhn_dist_create_mf(mfhn_op op, mfhn_mf m, const void *unique_id, mfhn_dist *out);
 void mfhn_dist_destroy(mfhn_dist d);
 int mfhn_dist_vmult(mfhn_dist d, void *dst, const void *src, void *cuda_stream, int zero_dst);
 int64_t mfhn_dist_launch_count(mfhn_dist d);
