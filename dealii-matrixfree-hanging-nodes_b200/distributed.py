@@ -110,21 +110,26 @@ class GhostExchange:
         uid = uid.to(self.device)
         dist.broadcast(uid, src=self._global_rank(0), group=self.group)
         uid = uid.cpu().contiguous()
-        ip = np.array(self.import_peers, dtype=np.int32)
-        ioff = np.zeros(len(ip) + 1, dtype=np.int64)
-        for i, p in enumerate(self.import_peers):
-            ioff[i + 1] = ioff[i] + len(part.import_indices[p])
-        iidx = (np.concatenate([part.import_indices[p] for p in self.import_peers]).astype(np.int32) if len(ip)
-                else np.zeros(0, dtype=np.int32))
-        gp = np.array(self.ghost_peers, dtype=np.int32)
-        gb = np.array([part.ghost_ranges[p][0] for p in self.ghost_peers], dtype=np.int64)
-        ge = np.array([part.ghost_ranges[p][1] for p in self.ghost_peers], dtype=np.int64)
-        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        desc = capi.DistDesc(rank=rank, world=world, unique_id=uid.data_ptr(), n_import_peers=len(ip), import_peers=ptr(ip),
-                             import_offsets=ptr(ioff), import_indices=ptr(iidx), n_ghost_peers=len(gp), ghost_peers=ptr(gp),
-                             ghost_begin=ptr(gb), ghost_end=ptr(ge), segments=(C.c_int64 * 4)(*self.seg))
         h = C.c_void_p()
-        check(lib.mfhn_dist_create(op._h, C.byref(desc), C.byref(h)))
+        mf = getattr(op, "mf", None)
+        if getattr(mf, "_h", None) is not None and part is mf.partitioner:
+            # the MatrixFree handle holds the partitioner and the cell partitions: one call
+            check(lib.mfhn_dist_create_mf(op._h, mf._h, uid.data_ptr(), C.byref(h)))
+        else:
+            ip = np.array(self.import_peers, dtype=np.int32)
+            ioff = np.zeros(len(ip) + 1, dtype=np.int64)
+            for i, p in enumerate(self.import_peers):
+                ioff[i + 1] = ioff[i] + len(part.import_indices[p])
+            iidx = (np.concatenate([part.import_indices[p] for p in self.import_peers]).astype(np.int32) if len(ip)
+                    else np.zeros(0, dtype=np.int32))
+            gp = np.array(self.ghost_peers, dtype=np.int32)
+            gb = np.array([part.ghost_ranges[p][0] for p in self.ghost_peers], dtype=np.int64)
+            ge = np.array([part.ghost_ranges[p][1] for p in self.ghost_peers], dtype=np.int64)
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            desc = capi.DistDesc(rank=rank, world=world, unique_id=uid.data_ptr(), n_import_peers=len(ip), import_peers=ptr(ip),
+                                 import_offsets=ptr(ioff), import_indices=ptr(iidx), n_ghost_peers=len(gp), ghost_peers=ptr(gp),
+                                 ghost_begin=ptr(gb), ghost_end=ptr(ge), segments=(C.c_int64 * 4)(*self.seg))
+            check(lib.mfhn_dist_create(op._h, C.byref(desc), C.byref(h)))
         self._native = h
 
     def __del__(self):

@@ -7,9 +7,14 @@
 //   GridGenerator::create_annulus(tria, L)             (benchmark_03.h:397-404)
 //   DoFHandler<3> dof_handler(tria);                 mfhn::DoFHandler dof_handler(tria, degree)
 //   dof_handler.distribute_dofs(FE_Q<3>(degree))       (benchmark_03.h:438-439)
+//   MatrixFree<3,Number> matrix_free;                mfhn::MatrixFree matrix_free(dof_handler, rank)
+//     matrix_free.reinit(mapping, dof_handler, ...)      (benchmark_03.h:326-340; cell order, categorisation,
+//                                                         rank-local numbering and partitioner come from the library)
 //   LaplaceOperator<3,degree,Number,MemorySpace::CUDA> mfhn::LaplaceOperator<3, degree, Number>
-//     op(mapping, dof_handler, constraints, quad, ac)    op(dof_handler, apply_constraints)
+//     op(mapping, dof_handler, constraints, quad, ac)    op(matrix_free, apply_constraints)
 //   op.initialize_dof_vector(v); op.vmult(dst, src)  identical                (benchmark_03.h:342-353)
+//   (ghost exchange inside cell_loop)                op.attach_communicator(unique_id): NCCL import / compress
+//                                                         overlapped with the interior cells (mfhn_dist_vmult)
 //
 // Non-zero C status codes become exceptions, mirroring the reference's
 // AssertThrow(..., ExcMessage / ExcNotImplemented()) convention.
@@ -70,24 +75,83 @@ private:
 class DoFHandler
 {
 public:
-  DoFHandler(const Triangulation &tria, int fe_degree)
+  // n_ranks > 1: rank-major numbering of the Morton (p4est) partition, optionally weighted (benchmark_02.cc:15-37)
+  DoFHandler(const Triangulation &tria, int fe_degree, int n_ranks = 1, double hn_weight = 1.0)
     : tria_(tria)
     , degree_(fe_degree)
+    , n_ranks_(n_ranks)
   {
-    check(mfhn_dofs_create(tria.handle(), fe_degree, 1, nullptr, &h_));
+    if (n_ranks > 1)
+      {
+        std::vector<int32_t> rank_of_cell(tria.n_global_active_cells());
+        check(mfhn_mesh_partition(tria.handle(), n_ranks, hn_weight, rank_of_cell.data()));
+        check(mfhn_dofs_create(tria.handle(), fe_degree, n_ranks, rank_of_cell.data(), &h_));
+      }
+    else
+      check(mfhn_dofs_create(tria.handle(), fe_degree, 1, nullptr, &h_));
   }
   ~DoFHandler() { mfhn_dofs_destroy(h_); }
   DoFHandler(const DoFHandler &) = delete;
   DoFHandler &operator=(const DoFHandler &) = delete;
   int64_t n_dofs() const { return mfhn_dofs_n_dofs(h_); }
   int degree() const { return degree_; }
+  int n_ranks() const { return n_ranks_; }
   const Triangulation &get_triangulation() const { return tria_; }
   mfhn_dofs handle() const { return h_; }
 
 private:
   const Triangulation &tria_;
-  int degree_;
+  int degree_, n_ranks_;
   mfhn_dofs h_ = nullptr;
+};
+
+// MatrixFree::reinit for one rank (mfhn_mf_create): benchmark_03.h:326-340, benchmark_01.h:251-284
+class MatrixFree
+{
+public:
+  explicit MatrixFree(const DoFHandler &dof_handler, int rank = 0, bool categorize = true)
+    : dof_handler_(dof_handler)
+  {
+    mfhn_mf_options opt{};
+    opt.rank       = rank;
+    opt.categorize = categorize ? 1 : 0;
+    check(mfhn_mf_create(dof_handler.handle(), &opt, &h_));
+    check(mfhn_mf_info(h_, &sizes_));
+  }
+  ~MatrixFree() { mfhn_mf_destroy(h_); }
+  MatrixFree(const MatrixFree &) = delete;
+  MatrixFree &operator=(const MatrixFree &) = delete;
+  const mfhn_mf_sizes &sizes() const { return sizes_; }
+  const DoFHandler &get_dof_handler() const { return dof_handler_; }
+  // global indices this rank ghosts from `peer` (peer = ghost peer number p < n_ghost_peers): rank and index list
+  int ghost_peer(int p, const int64_t *&indices, int64_t &n) const
+  {
+    const int32_t *peers;
+    const int64_t *gb, *ge, *ghost_global;
+    check(mfhn_mf_partitioner(h_, &peers, &gb, &ge, nullptr, nullptr, nullptr, nullptr));
+    check(mfhn_mf_arrays(h_, nullptr, nullptr, nullptr, nullptr, &ghost_global, nullptr));
+    indices = ghost_global + gb[p];
+    n       = ge[p] - gb[p];
+    return peers[p];
+  }
+  void set_imports(int peer, const int64_t *global_indices, int64_t n)
+  {
+    check(mfhn_mf_set_imports(h_, peer, global_indices, n));
+    check(mfhn_mf_info(h_, &sizes_));
+  }
+  // support points of the locally owned DoFs (VectorTools::interpolate, benchmark_03.h:455-468)
+  std::vector<double> owned_support_points() const
+  {
+    std::vector<double> xyz(3 * (size_t)sizes_.n_owned);
+    check(mfhn_dofs_support_points(dof_handler_.handle(), sizes_.owned_begin, sizes_.owned_begin + sizes_.n_owned, xyz.data()));
+    return xyz;
+  }
+  mfhn_mf handle() const { return h_; }
+
+private:
+  const DoFHandler &dof_handler_;
+  mfhn_mf h_ = nullptr;
+  mfhn_mf_sizes sizes_{};
 };
 
 // LinearAlgebra::distributed::Vector<Number, MemorySpace::CUDA> for one rank
@@ -109,8 +173,10 @@ public:
   }
   Vector &operator=(Number v)
   {
-    if (v != Number(0)) throw ExcNotImplemented("only zero assignment");
-    cudaMemset(d_, 0, sizeof(Number) * n_);
+    if (v == Number(0))
+      cudaMemset(d_, 0, sizeof(Number) * n_);
+    else
+      import_from_host(std::vector<Number>((size_t)n_, v));
     return *this;
   }
   void import_from_host(const std::vector<Number> &h) { cudaMemcpy(d_, h.data(), sizeof(Number) * n_, cudaMemcpyHostToDevice); }
@@ -139,47 +205,34 @@ public:
 
   // benchmark_03.h:326-340.  Mapping is MappingQ1 on Cartesian cells, constraints are empty
   // and the quadrature is QGauss<1>(fe_degree + 1), exactly as in the reference driver.
-  LaplaceOperator(const DoFHandler &dof_handler, const bool apply_constraints, const int kernel = MFHN_KERNEL_AUTO)
+  LaplaceOperator(const MatrixFree &matrix_free, const bool apply_constraints, const int kernel = MFHN_KERNEL_AUTO)
+    : matrix_free_(matrix_free)
   {
-    if (dof_handler.degree() != fe_degree) throw ExcMessage("Degrees do not match!"); // benchmark_01.h:204-206
-    const Triangulation &tria = dof_handler.get_triangulation();
-    const int64_t n_cells     = tria.n_global_active_cells();
-    // MatrixFree reorders its cell batches: visit the cells along the Morton curve
-    const std::vector<int64_t> pos = tria.morton_position();
-    std::vector<int64_t> cells(n_cells);
-    for (int64_t c = 0; c < n_cells; ++c) cells[pos[c]] = c;
-    const int64_t n3 = (int64_t)(fe_degree + 1) * (fe_degree + 1) * (fe_degree + 1);
-    std::vector<uint64_t> global((size_t)n_cells * n3);
-    std::vector<uint8_t> masks(n_cells);
-    std::vector<double> h(n_cells);
-    check(mfhn_dofs_fill(dof_handler.handle(), n_cells, cells.data(), nullptr, global.data(), masks.data(), h.data()));
-    std::vector<uint32_t> local(global.begin(), global.end());
-    n_dofs_ = dof_handler.n_dofs();
-    mfhn_op_desc d{};
-    d.degree            = fe_degree;
-    d.number            = sizeof(Number) == 8 ? MFHN_F64 : MFHN_F32;
-    d.n_cells           = n_cells;
-    d.n_owned           = n_dofs_;
-    d.n_ghost           = 0;
-    d.dof_indices       = local.data();
-    d.masks             = masks.data();
-    d.geometry_type     = MFHN_GEOM_CARTESIAN;
-    d.geometry          = h.data();
-    d.apply_constraints = apply_constraints;
-    d.kernel            = kernel;
-    d.device            = -1;
-    check(mfhn_op_create(&d, &op_));
+    if (matrix_free.sizes().degree != fe_degree) throw ExcMessage("Degrees do not match!"); // benchmark_01.h:204-206
+    check(mfhn_op_create_mf(matrix_free.handle(), sizeof(Number) == 8 ? MFHN_F64 : MFHN_F32, kernel, apply_constraints, -1, &op_));
   }
-  ~LaplaceOperator() { mfhn_op_destroy(op_); }
+  ~LaplaceOperator()
+  {
+    if (dist_) mfhn_dist_destroy(dist_);
+    mfhn_op_destroy(op_);
+  }
+  // partitioned operator: unique_id = 128 bytes from mfhn_dist_unique_id on rank 0, the same on every rank; the
+  // import lists of the MatrixFree must be set (MatrixFree::set_imports)
+  void attach_communicator(const void *unique_id) { check(mfhn_dist_create_mf(op_, matrix_free_.handle(), unique_id, &dist_)); }
   LaplaceOperator(const LaplaceOperator &) = delete;
   LaplaceOperator &operator=(const LaplaceOperator &) = delete;
 
-  void initialize_dof_vector(VectorType &vec) const { vec.reinit(n_dofs_); }
+  // owned entries first, ghost entries behind them (LinearAlgebra::distributed::Vector layout)
+  void initialize_dof_vector(VectorType &vec) const { vec.reinit(matrix_free_.sizes().n_owned + matrix_free_.sizes().n_ghost); }
 
-  // accumulates into dst like cell_loop(local_operator, src, dst) (benchmark_03.h:348-353); asynchronous
+  // accumulates into dst like cell_loop(local_operator, src, dst) (benchmark_03.h:348-353); asynchronous.
+  // With a communicator: ghost import, three cell partitions and ghost compress in one call.
   void vmult(VectorType &dst, const VectorType &src, cudaStream_t stream = nullptr) const
   {
-    check(mfhn_op_vmult(op_, dst.data(), src.data(), stream, 0));
+    if (dist_)
+      check(mfhn_dist_vmult(dist_, dst.data(), src.data(), stream, 0));
+    else
+      check(mfhn_op_vmult(op_, dst.data(), src.data(), stream, 0));
   }
   double query(const char *what) const
   {
@@ -189,7 +242,8 @@ public:
   }
 
 private:
-  mfhn_op op_ = nullptr;
-  int64_t n_dofs_ = 0;
+  const MatrixFree &matrix_free_;
+  mfhn_op op_     = nullptr;
+  mfhn_dist dist_ = nullptr;
 };
 } // namespace mfhn

@@ -181,9 +181,113 @@ def test_symmetry_and_energy_large(mfhn):
         assert abs(b[live] @ Aa[live] - a[live] @ Ab[live]) / abs(b[live] @ Aa[live]) < 1e-10
 
 
+def _metric(J):
+    """det J J^-1 J^-T of [..., 3, 3] Jacobians as the six components (xx,xy,xz,yy,yz,zz)."""
+    Ji = np.linalg.inv(J)
+    M = np.linalg.det(J)[..., None, None] * (Ji @ np.swapaxes(Ji, -1, -2))
+    return np.stack([M[..., 0, 0], M[..., 0, 1], M[..., 0, 2], M[..., 1, 1], M[..., 1, 2], M[..., 2, 2]], axis=-1)
+
+
+def _oracle_layout_in_operator_order(mfhn, mf, lay, geo, L, flavour):
+    """The oracle's layout with the cells in the operator's (reordered) cell order."""
+    import copy
+
+    perm = {tuple(c): i for i, c in enumerate(lay.cells.tolist())}
+    cells = mfhn.Triangulation(geo, L, flavour).cells()[mf.cell_ids]
+    order = np.array([perm[tuple(c)] for c in cells.tolist()])
+    lo = copy.copy(lay)
+    lo.cells, lo.dof_indices, lo.kinds, lo.masks, lo.h = lay.cells[order], lay.dof_indices[order], lay.kinds[order], lay.masks[order], lay.h[order]
+    assert np.array_equal(lo.dof_indices, mf.dof_indices) and np.array_equal(lo.masks, mf.masks)
+    return lo
+
+
+@pytest.mark.parametrize("k", [2, 4, 5])
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_affine_geometry_sheared_and_rotated(mfhn, k, number):
+    """MFHN_GEOM_AFFINE with full 3x3 Jacobians (shear + rotation + anisotropic scaling, different per cell): all six
+    components of det J J^-1 J^-T are non-zero.  Against the numpy restatement of evaluate / submit_gradient / integrate
+    (benchmark_03.h:284-290) with the same coefficient at every quadrature point."""
+    import torch
+
+    from oracle import fe1d
+
+    geo, L = ("annulus", 5) if k <= 4 else ("quadrant", 4)
+    dh, mf, lay = _case(mfhn, geo, L, "serial", k)
+    lo = _oracle_layout_in_operator_order(mfhn, mf, lay, geo, L, "serial")
+    n = k + 1
+    rng = np.random.default_rng(3)
+    th = rng.uniform(0, 2 * np.pi, mf.n_cells)
+    Rz = np.zeros((mf.n_cells, 3, 3))
+    Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1], Rz[:, 2, 2] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th), 1.0
+    shear = np.array([[1.0, 0.35, -0.2], [0.1, 1.2, 0.25], [-0.15, 0.3, 0.8]])
+    J = mf.h[:, None, None] * (Rz @ (shear[None] + rng.uniform(-0.05, 0.05, (mf.n_cells, 3, 3))))
+    assert (np.linalg.det(J) > 0).all()
+    w = fe1d.shape_data(k).qw
+    w3 = (w[:, None, None] * w[None, :, None] * w[None, None, :]).ravel()
+    G = np.einsum("cm,q->cmq", _metric(J), w3)
+    assert min(np.abs(G[:, comp]).max() for comp in (1, 2, 4)) > 1e-3  # the off-diagonal terms are live
+    x = _src(lay, "random")
+    ref = operators.vmult_general(lo, x, G)
+    for kernel in ("auto", "qpoint"):
+        op = mfhn.LaplaceOperator(mf, number=number, kernel=kernel, geometry=J)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.copy_(torch.from_numpy(x).to(src.dtype))
+        op.vmult(dst, src)
+        err = np.abs(dst.cpu().numpy().astype(np.float64) - ref).max() / np.abs(ref).max()
+        assert err < TOL[number], (k, number, kernel, err)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 6])
+def test_general_geometry_full_tensor(mfhn, k):
+    """MFHN_GEOM_GENERAL with a deformation whose Jacobian is a full matrix at every quadrature point
+    (x = X + eps d(X), d mixes the coordinates): xy / xz / yz coefficients are non-zero and vary inside the cell --
+    the data class of TestHighOrderMapping (benchmark_01.h:225-242, benchmark_03.h:284-290)."""
+    import torch
+
+    from oracle import fe1d
+
+    geo, L = ("annulus", 5) if k <= 4 else ("quadrant", 4)
+    dh, mf, lay = _case(mfhn, geo, L, "serial", k)
+    lo = _oracle_layout_in_operator_order(mfhn, mf, lay, geo, L, "serial")
+    n = k + 1
+    sd = fe1d.shape_data(k)
+    q, w = sd.qpts, sd.qw
+    w3 = (w[:, None, None] * w[None, :, None] * w[None, None, :]).ravel()
+    hh = lo.h
+    org = -1.0 + lo.cells[:, 1:4] * hh[:, None]
+    qx, qy, qz = np.tile(q, n * n), np.tile(np.repeat(q, n), n), np.repeat(q, n * n)
+    X, Y, Z = (org[:, d, None] + hh[:, None] * qq[None, :] for d, qq in enumerate((qx, qy, qz)))
+    eps, pi = 2e-2, np.pi
+    # d = (sin(pi Y) + sin(pi Z), sin(pi X) cos(pi Z), sin(pi (X + Y))): gradient of the deformation at the quadrature points
+    D = np.zeros(X.shape + (3, 3))
+    D[..., 0, 1], D[..., 0, 2] = pi * np.cos(pi * Y), pi * np.cos(pi * Z)
+    D[..., 1, 0], D[..., 1, 2] = pi * np.cos(pi * X) * np.cos(pi * Z), -pi * np.sin(pi * X) * np.sin(pi * Z)
+    D[..., 2, 0] = D[..., 2, 1] = pi * np.cos(pi * (X + Y))
+    J = hh[:, None, None, None] * (np.eye(3) + eps * D)
+    assert (np.linalg.det(J) > 0).all()
+    G = np.moveaxis(_metric(J), -1, 1) * w3[None, None, :]  # [cell][6][q]
+    assert min(np.abs(G[:, comp]).max() for comp in (1, 2, 4)) > 1e-4
+    x = _src(lay, "random")
+    ref = operators.vmult_general(lo, x, G)
+    for kernel in ("auto", "qpoint"):
+        op = mfhn.LaplaceOperator(mf, kernel=kernel, geometry=G)
+        src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.copy_(torch.from_numpy(x))
+        op.vmult(dst, src)
+        y = dst.cpu().numpy()
+        assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12, (k, kernel)
+    # symmetry and null space survive the full tensor
+    b = np.random.default_rng(9).uniform(-1, 1, lay.n_dofs)
+    Ab = operators.vmult_general(lo, b, G)
+    live = ref != 0
+    assert abs(b[live] @ y[live] - x[live] @ Ab[live]) < 1e-10 * abs(b[live] @ y[live])
+    src.fill_(1.0)
+    op.vmult(dst, src, zero_dst=True)
+    assert dst.abs().max().item() < 1e-10
+
+
 def test_affine_geometry_matches_cartesian(mfhn):
-    """Affine path with J = h I must reproduce the Cartesian result; a sheared J
-    must stay symmetric and keep constants in the null space."""
+    """Affine path with J = h I must reproduce the Cartesian result."""
     import torch
 
     dh, mf, lay = _case(mfhn, "annulus", 5, "serial", 2)
@@ -250,7 +354,14 @@ def test_cpp_driver_over_c_abi(mfhn):
     ref = np.linalg.norm(operators.vmult_fast(lay, np.sin(lay.support_points).sum(axis=1)))
     assert abs(got - ref) / ref < 1e-10
     cols = out.splitlines()[1].split()
-    assert int(cols[3]) == lay.n_cells and int(cols[5]) == lay.n_dofs and int(cols[4]) == int((lay.masks != 0).sum())
+    assert int(cols[0]) == 1 and int(cols[4]) == lay.n_cells and int(cols[6]) == lay.n_dofs and int(cols[5]) == int((lay.masks != 0).sum())
+    # the reference's `mpirun -np 2`: forked ranks, one GPU each, NCCL ghost exchange (needs two devices)
+    import torch
+
+    if torch.cuda.device_count() >= 2:
+        out = subprocess.run([exe, "annulus", "3", "5", "5", "2"], check=True, capture_output=True, text=True).stdout
+        got = float(re.search(r"n_repetitions = ([0-9.e+-]+)", out).group(1))
+        assert abs(got - ref) / ref < 1e-10
 
 
 def test_host_vector_entry_point(mfhn):
