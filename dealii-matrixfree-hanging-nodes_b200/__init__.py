@@ -14,7 +14,7 @@ from . import _capi as capi
 from ._capi import MfhnError, NotImplementedMfhn
 from .api import (DoFHandler, LaplaceOperator, MatrixFree, Partitioner, Triangulation, bench_fma,
                   exchange_import_indices, exchange_local)
-from .solvers import solve_cg
+from .solvers import inverse_diagonal, solve_cg
 
 __all__ = ["capi", "MfhnError", "NotImplementedMfhn", "Triangulation", "DoFHandler", "MatrixFree",
-           "Partitioner", "LaplaceOperator", "bench_fma", "exchange_import_indices", "exchange_local", "solve_cg"]
+           "Partitioner", "LaplaceOperator", "bench_fma", "exchange_import_indices", "exchange_local", "solve_cg", "inverse_diagonal"]

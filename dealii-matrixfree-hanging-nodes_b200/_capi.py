@@ -39,6 +39,7 @@ class OpDesc(C.Structure):
         ("device", c_int),
         ("segments", c_void_p),
         ("n_segments", c_int),
+        ("vector_padding", c_int),
     ]
 
 
@@ -50,6 +51,15 @@ class MfSizes(C.Structure):
     _fields_ = [("degree", c_int), ("rank", c_int), ("n_ranks", c_int), ("n_cells", c_int64), ("n_cells_hn", c_int64),
                 ("n_owned", c_int64), ("n_ghost", c_int64), ("owned_begin", c_int64), ("n_interior_a", c_int64),
                 ("n_interior", c_int64), ("n_ghost_peers", c_int), ("n_import_peers", c_int), ("n_import", c_int64)]
+
+
+class CgOptions(C.Structure):
+    _fields_ = [("max_iter", c_int), ("rel_tol", c_double), ("check_every", c_int), ("timings", c_int)]
+
+
+class CgResult(C.Structure):
+    _fields_ = [("iterations", c_int), ("initial_residual", c_double), ("final_residual", c_double), ("ms_total", c_double),
+                ("ms_vmult", c_double), ("ms_vector_ops", c_double), ("ms_allreduce", c_double)]
 
 
 class DistDesc(C.Structure):
@@ -101,6 +111,7 @@ SIGNATURES = {
     "mfhn_check_kind": (c_int, [C.c_uint16]),
     "mfhn_op_create": (c_int, [P(OpDesc), P(c_void_p)]),
     "mfhn_op_create_mf": (c_int, [c_void_p, c_int, c_int, c_int, c_int, P(c_void_p)]),
+    "mfhn_op_create_mf_padded": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, P(c_void_p)]),
     "mfhn_op_destroy": (None, [c_void_p]),
     "mfhn_op_vmult": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "mfhn_op_vmult_range": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64]),
@@ -122,12 +133,15 @@ SIGNATURES = {
     "mfhn_dist_destroy": (None, [c_void_p]),
     "mfhn_dist_vmult": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "mfhn_dist_launch_count": (c_int64, [c_void_p]),
+    "mfhn_op_inverse_diagonal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mfhn_cg_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(CgOptions), P(CgResult), c_void_p, c_void_p]),
     "mfhn_vec_alloc": (c_int, [c_int64, P(c_void_p)]),
     "mfhn_vec_free": (c_int, [c_void_p]),
     "mfhn_ipc_get_handle": (c_int, [c_void_p, c_void_p]),
     "mfhn_ipc_open_handle": (c_int, [c_void_p, P(c_void_p)]),
     "mfhn_ipc_close_handle": (c_int, [c_void_p]),
     "mfhn_dist_enable_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mfhn_dist_enable_peer_flags": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mfhn_dist_vmult_peer": (c_int, [c_void_p, c_void_p, c_int]),
 }
 
@@ -156,6 +170,7 @@ def check(status: int):
 
 
 F64, F32 = 0, 1
+VECTOR_PADDING = 4  # MFHN_VECTOR_PADDING: spare entries behind every vector handed to a padded operator
 SERIAL, P4EST = 0, 1
 GEOM_CARTESIAN, GEOM_AFFINE, GEOM_GENERAL = 0, 1, 2
 KERNEL_AUTO, KERNEL_QPOINT, KERNEL_SEPARABLE, KERNEL_BASELINE, KERNEL_PLANE, KERNEL_PATCH = 0, 1, 2, 3, 4, 5

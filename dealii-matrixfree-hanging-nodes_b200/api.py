@@ -301,7 +301,8 @@ class LaplaceOperator:
             degree=matrix_free.degree, number=self.number, n_cells=matrix_free.n_cells, n_owned=part.n_owned,
             n_ghost=part.n_ghost, dof_indices=_ptr(matrix_free.dof_indices), masks=_ptr(matrix_free.masks),
             geometry_type=gtype, geometry=_ptr(geom), apply_constraints=int(apply_constraints), kernel=kern,
-            device=self.device.index, segments=_ptr(self._segments), n_segments=len(self._segments))
+            device=self.device.index, segments=_ptr(self._segments), n_segments=len(self._segments),
+            vector_padding=capi.VECTOR_PADDING)
         h = C.c_void_p()
         check(lib.mfhn_op_create(C.byref(desc), C.byref(h)))
         self._h = h
@@ -315,7 +316,14 @@ class LaplaceOperator:
 
     # -- reference surface ---------------------------------------------------
     def initialize_dof_vector(self):
-        return _torch().zeros(self.n_owned + self.n_ghost, dtype=self.dtype, device=self.device)
+        """n_owned + n_ghost entries (LinearAlgebra::distributed::Vector layout, benchmark_03.h:342-346) with
+        MFHN_VECTOR_PADDING spare entries behind them in the same allocation: the bulk-copy kernel moves 16-byte
+        aligned ranges, and the range of the block that ends the vector reaches past the last entry."""
+        n = self.n_owned + self.n_ghost
+        return _torch().zeros(n + capi.VECTOR_PADDING, dtype=self.dtype, device=self.device)[:n]
+
+    def _padded(self, v):
+        return v.untyped_storage().nbytes() >= (v.storage_offset() + v.numel() + capi.VECTOR_PADDING) * v.element_size()
 
     def vmult(self, dst, src, zero_dst=False):
         torch = _torch()
@@ -356,6 +364,7 @@ class LaplaceOperator:
 
     def vmult_range(self, dst, src, cell_begin, cell_end):
         torch = _torch()
+        self._check_vec(dst), self._check_vec(src)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         check(lib.mfhn_op_vmult_range(self._h, dst.data_ptr(), src.data_ptr(), stream, cell_begin, cell_end))
 
@@ -380,8 +389,8 @@ class LaplaceOperator:
         check(lib.mfhn_op_apply_hn(self._h, cell_values.data_ptr(), int(transpose), stream))
 
     def _check_vec(self, v):
-        if not (v.is_cuda and v.dtype == self.dtype and v.is_contiguous() and v.numel() == self.n_owned + self.n_ghost):
-            raise capi.MfhnError(1, "vector must come from initialize_dof_vector()")
+        if not (v.is_cuda and v.dtype == self.dtype and v.is_contiguous() and v.numel() == self.n_owned + self.n_ghost and self._padded(v)):
+            raise capi.MfhnError(1, "vector must come from initialize_dof_vector() (n_owned + n_ghost entries plus padding)")
 
     def attach_communicator(self, comm):
         self._comm = comm

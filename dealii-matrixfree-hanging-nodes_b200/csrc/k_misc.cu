@@ -161,7 +161,34 @@ __global__ void unpack_add_kernel(Number *vec, const Number *buf, const int32_t 
         vec[idx[i]] += buf[i];
     }
 }
+// Barrier between the ranks (one process per GPU) of a peer-memory operator.  flags = unsigned[world + 1] in memory that
+// the peers have mapped (CUDA IPC): slot r = last epoch rank r has announced here, entry `world` = this rank's epoch
+// counter.  Thread p announces the new epoch in peer p's array (release, system scope: everything earlier kernels of
+// this stream wrote -- also over NVLink -- is visible first), then waits until peer p has announced it here.
+// All ranks call it the same number of times.
+__global__ void peer_barrier_kernel(unsigned *flags, unsigned *const *peer_flags, const int rank, const int world)
+{
+  __shared__ unsigned epoch;
+  if (threadIdx.x == 0) epoch = ++flags[world];
+  __syncthreads();
+  const int p = threadIdx.x;
+  if (p < world && p != rank)
+    {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(epoch) : "memory");
+      unsigned seen;
+      do
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + p) : "memory");
+      while ((int)(seen - epoch) < 0);
+    }
+}
 } // namespace
+
+void run_peer_barrier(unsigned *flags_local, unsigned *const *d_peer_flags, int rank, int world, cudaStream_t stream)
+{
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(flags_local, d_peer_flags, rank, world);
+  check_launch("peer barrier");
+}
 
 void run_baseline(int degree, int number, BaselineArrays &arrays, const uint32_t *d_idx, const void *d_h, long long n_cells, const CellLoopParams &p,
                   int device, cudaStream_t stream)

@@ -11,10 +11,7 @@ void run_plane_n(const PlaneLayout &L, const CellLoopParams &p, int device, cuda
   if constexpr (plane_supported(n))
     launch_plane<n, Number>(L, p, device, stream, peer);
   else
-    {
-      if (peer) throw std::runtime_error("peer mode covers the register-tiled plane kernel (degree <= 5)");
-      launch_plane_smem<n, Number>(L, p, device, stream);
-    }
+    launch_plane_smem<n, Number>(L, p, device, stream, peer);
 }
 template <typename Number>
 void run_plane_number(int degree, const PlaneLayout &L, const CellLoopParams &p, int device, cudaStream_t stream, const PeerTables *peer)

@@ -28,7 +28,7 @@ struct PlaneSmemCfg
 };
 
 
-template <int n, typename Number>
+template <int n, typename Number, bool PEER = false>
 __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_smem_kernel(const PlaneParams p)
 {
   using Cfg = PlaneSmemCfg<n, Number>;
@@ -69,7 +69,13 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
 #pragma unroll
       for (int r = 0; r < RF; ++r)
 #pragma unroll
-        for (int x = 0; x < n; ++x) v[r][x] = (valid && y0 + r < n) ? __ldg(src + idx[r][x]) : Number(0);
+        for (int x = 0; x < n; ++x)
+          {
+            if (PEER && valid && y0 + r < n && idx[r][x] >= (uint32_t)p.n_owned) // remote entry: plain load through the peer mapping
+              v[r][x] = *static_cast<const Number *>(p.ghost_src[idx[r][x] - (uint32_t)p.n_owned]);
+            else
+              v[r][x] = (valid && y0 + r < n) ? __ldg(src + idx[r][x]) : Number(0);
+          }
 #pragma unroll
       for (int r = 0; r < RF; ++r)
         if (y0 + r < n)
@@ -180,22 +186,36 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
       if (active && valid)
         {
 #pragma unroll
-          for (int x = 0; x < n; ++x) atomicAdd(dst + g[x], u[x]);
+          for (int x = 0; x < n; ++x)
+            {
+              if (PEER && g[x] >= (uint32_t)p.n_owned) // red over NVLink into the owner's dst
+                atomicAdd(static_cast<Number *>(p.ghost_dst[g[x] - (uint32_t)p.n_owned]), u[x]);
+              else
+                atomicAdd(dst + g[x], u[x]);
+            }
         }
     }
 }
 
-template <int n, typename Number>
-void launch_plane_smem(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream)
+template <int n, typename Number, bool PEER>
+void launch_plane_smem_variant(const PlaneParams &p, const unsigned grid, int device, cudaStream_t stream)
 {
   using Cfg = PlaneSmemCfg<n, Number>;
   static bool attr[64] = {};
   if (!attr[device])
     {
-      cudaError_t e = cudaFuncSetAttribute(plane_smem_kernel<n, Number>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
+      cudaError_t e = cudaFuncSetAttribute(plane_smem_kernel<n, Number, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem);
       if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       attr[device] = true;
     }
+  plane_smem_kernel<n, Number, PEER><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+}
+
+template <int n, typename Number>
+void launch_plane_smem(const PlaneLayout &L, const CellLoopParams &cp, int device, cudaStream_t stream, const PeerTables *peer = nullptr)
+{
+  using Cfg = PlaneSmemCfg<n, Number>;
+  if (device < 0 || device >= 64) throw std::runtime_error("device ordinal out of range");
   PlaneParams p;
   p.pidx              = L.d_pidx;
   p.masks             = cp.masks;
@@ -207,10 +227,16 @@ void launch_plane_smem(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.batch_begin       = cp.cell_begin / Cfg::cpw;
   p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
+  p.n_owned           = peer ? peer->n_owned : 0;
+  p.ghost_src         = peer ? peer->ghost_src : nullptr;
+  p.ghost_dst         = peer ? peer->ghost_dst : nullptr;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + Cfg::warps - 1) / Cfg::warps);
-  plane_smem_kernel<n, Number><<<grid, Cfg::warps * 32, Cfg::smem, stream>>>(p);
+  if (peer)
+    launch_plane_smem_variant<n, Number, true>(p, grid, device, stream);
+  else
+    launch_plane_smem_variant<n, Number, false>(p, grid, device, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("plane (smem) kernel launch: ") + cudaGetErrorString(e));
 }

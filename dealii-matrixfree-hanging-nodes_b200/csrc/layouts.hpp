@@ -91,7 +91,8 @@ constexpr bool bulk_supported(int n) { return n >= 4 && n <= 6; }
 // ---- launch entry points (degree = k, number = MFHN_F64 / MFHN_F32); they throw std::runtime_error ----
 // k_generic_*.cu
 void run_generic(int degree, int number, int variant, bool diag, const CellLoopParams &p, int device, cudaStream_t stream);
-// k_plane.cu: register-tiled kernel for k <= 5, shared-memory plane kernel above; peer != nullptr: k <= 5 only
+// k_plane.cu: register-tiled kernel for k <= 5, shared-memory plane kernel above; peer != nullptr: ghost entries are
+// read from / added to the owners' vectors through peer-mapped pointers
 void run_plane(int degree, int number, const PlaneLayout &L, const CellLoopParams &p, int device, cudaStream_t stream, const PeerTables *peer);
 // k_bulk.cu
 void run_bulk(int degree, int number, const BulkLayout &L, const CellLoopParams &p, int device, cudaStream_t stream);
@@ -104,4 +105,14 @@ void run_hn_only(int degree, int number, void *values, const uint8_t *d_masks, l
 double run_fma_bench(int number, int iters);
 void run_pack(int number, void *buffer, const void *vec, const int32_t *idx, long long n, cudaStream_t stream);
 void run_unpack_add(int number, void *vec, const void *buffer, const int32_t *idx, long long n, bool atomic, cudaStream_t stream);
+// barrier between the ranks of a peer-memory operator: flags in each other's (IPC-mapped) memory, see k_misc.cu
+void run_peer_barrier(unsigned *flags_local, unsigned *const *d_peer_flags, int rank, int world, cudaStream_t stream);
+// k_cg.cu: fused vector kernels of the Chronopoulos / Gear CG iteration
+size_t cg_scalars_bytes();
+void run_cg_dots(int number, const void *r, const void *u, const void *w, long long n, void *scalars, cudaStream_t stream);
+void run_cg_scalars(void *scalars, double *history, cudaStream_t stream);
+void run_cg_update(int number, void *p, void *s, void *x, void *r, void *u, const void *w, const void *inv_diag, long long n, const void *scalars,
+                   cudaStream_t stream);
+void run_cg_residual(int number, void *r, void *u, const void *b, const void *inv_diag, long long n, cudaStream_t stream);
+void run_invert_diagonal(int number, void *d, long long n, cudaStream_t stream);
 } // namespace mfhn

@@ -97,6 +97,7 @@ struct Operator
   BaselineArrays baseline;      // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use)
   std::vector<long long> segments;
   long long launches = 0;
+  int vector_padding = 0; // valid entries behind n_owned + n_ghost in every vector (promise of the caller)
   void *d_stage_src[2] = {nullptr, nullptr}, *d_stage_dst[2] = {nullptr, nullptr}; // device staging of the host-vector entry point (2 slots)
 
   ~Operator()
@@ -307,7 +308,9 @@ Operator *op_create(const mfhn_op_desc &d)
           for (int i = 1; i < d.n_segments; ++i)
             if (d.segments[i] < d.segments[i - 1] || d.segments[i] > d.n_cells) throw InvalidArgument("segments must be ascending");
         }
-      if (bulk_supported(n)) bulk_build(op->bulk, n, d.number, d.n_cells, nvec, d.dof_indices);
+      if (d.vector_padding < 0) throw InvalidArgument("negative vector padding");
+      op->vector_padding = d.vector_padding;
+      if (bulk_supported(n)) bulk_build(op->bulk, n, d.number, d.n_cells, nvec + d.vector_padding, d.dof_indices);
     }
   resolve_kernel(*op);
   return op.release();
@@ -333,12 +336,15 @@ struct Dist
   void *peer_src_local = nullptr, *peer_dst_local = nullptr;
   void **d_ghost_src = nullptr, **d_ghost_dst = nullptr;
   int *d_barrier = nullptr;
+  // barriers of the peer path through flags in each other's memory instead of NCCL all-reduces
+  unsigned *flags_local = nullptr, **d_peer_flags = nullptr;
 
   ~Dist()
   {
     cudaFree(d_ghost_src);
     cudaFree(d_ghost_dst);
     cudaFree(d_barrier);
+    cudaFree(d_peer_flags);
     if (comm) NcclApi::get().CommDestroy(comm);
     cudaFree(d_import_idx);
     cudaFree(d_send);
@@ -386,6 +392,8 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   if (d.seg[1] > d.seg[0]) op_vmult_range(op, dst, src, main, d.seg[0], d.seg[1]); // interior A overlaps the import
   CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[1], 0));
   if (d.seg[3] > d.seg[2]) op_vmult_range(op, dst, src, main, d.seg[2], d.seg[3]); // boundary cells need the ghosts
+  // zero_out_ghost_values: the imported entries are scratch, a later use of src as dst must not send them to the owners
+  if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(srcb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
   CUDA_CHECK(cudaEventRecord(d.ev[2], main));
   CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[2], 0));
   // ghosts -> owners (compress, add)
@@ -408,10 +416,11 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(dstb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
 }
 
-// Peer-memory variant: no pack / unpack and no data-path collective.  After a barrier the
-// boundary cells read the owners' src entries and add into the owners' dst entries directly
-// over NVLink; a second barrier makes the remote contributions visible before anyone consumes
-// dst.  The barriers are 4-byte NCCL all-reduces.
+// Peer-memory variant (fused compute + exchange): no pack / unpack and no data-path collective.  After a barrier the
+// boundary cells read the owners' src entries and add into the owners' dst entries directly over NVLink; a second
+// barrier makes the remote contributions visible before anyone consumes dst.  The barriers are flag exchanges in each
+// other's memory (mfhn_dist_enable_peer_flags; pure CUDA, so the whole vmult can be captured in a CUDA graph) or,
+// without flags, 4-byte NCCL all-reduces.
 void dist_vmult_peer_n(Dist &d, cudaStream_t main)
 {
   Operator &op = *d.op;
@@ -426,14 +435,11 @@ void dist_vmult_peer_n(Dist &d, cudaStream_t main)
   pt.n_owned   = op.n_owned;
   pt.ghost_src = d.d_ghost_src;
   pt.ghost_dst = d.d_ghost_dst;
-  NcclApi &nccl = NcclApi::get();
-  auto launch = [&](long long cb, long long ce, const PeerTables *peer, cudaStream_t st) {
-    if (ce <= cb) return;
-    p.cell_begin = cb;
-    p.cell_end   = ce;
-    if (op.degree > 5) throw NotImplemented("peer mode covers the register-tiled plane kernel (degree <= 5)");
-    run_plane(op.degree, op.number, op.plane, p, op.device, st, peer);
-    ++op.launches;
+  auto barrier = [&]() {
+    if (d.flags_local)
+      run_peer_barrier(d.flags_local, d.d_peer_flags, d.rank, d.world, d.comm_stream);
+    else
+      NCCL_CHECK(NcclApi::get().AllReduce(d.d_barrier, d.d_barrier, 1, 2 /*ncclInt32*/, 0 /*ncclSum*/, d.comm, d.comm_stream));
     ++d.launches;
   };
   // high-priority stream: barrier (peers' src final, peers' dst zeroed) -> boundary cells with remote
@@ -441,11 +447,24 @@ void dist_vmult_peer_n(Dist &d, cudaStream_t main)
   // only) run concurrently on the compute stream and hide the whole chain
   CUDA_CHECK(cudaEventRecord(d.ev[0], main));
   CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[0], 0));
-  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2 /*ncclInt32*/, 0 /*ncclSum*/, d.comm, d.comm_stream));
-  launch(d.seg[2], d.seg[3], &pt, d.comm_stream);
-  NCCL_CHECK(nccl.AllReduce(d.d_barrier, d.d_barrier, 1, 2, 0, d.comm, d.comm_stream));
+  barrier();
+  if (d.seg[3] > d.seg[2])
+    {
+      // boundary cells: plane kernel with peer tables (register-tiled for k <= 5, plane in shared memory above)
+      p.cell_begin = d.seg[2];
+      p.cell_end   = d.seg[3];
+      run_plane(op.degree, op.number, op.plane, p, op.device, d.comm_stream, &pt);
+      ++op.launches;
+      ++d.launches;
+    }
+  barrier();
   CUDA_CHECK(cudaEventRecord(d.ev[3], d.comm_stream));
-  launch(d.seg[0], d.seg[2], nullptr, main);
+  if (d.seg[2] > d.seg[0])
+    {
+      const long long before = op.launches;
+      op_vmult_range(op, d.peer_dst_local, d.peer_src_local, main, d.seg[0], d.seg[2]); // the operator's own kernel (bulk copies at k = 4, 5)
+      d.launches += op.launches - before;
+    }
   CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
 }
 } // namespace mfhn
@@ -461,6 +480,10 @@ int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out)
   });
 }
 int mfhn_op_create_mf(mfhn_mf m, int number, int kernel, int apply_constraints, int device, mfhn_op *out)
+{
+  return mfhn_op_create_mf_padded(m, number, kernel, apply_constraints, device, 0, out);
+}
+int mfhn_op_create_mf_padded(mfhn_mf m, int number, int kernel, int apply_constraints, int device, int vector_padding, mfhn_op *out)
 {
   return guard([&] {
     if (!m || !out) throw InvalidArgument("null argument");
@@ -484,6 +507,7 @@ int mfhn_op_create_mf(mfhn_mf m, int number, int kernel, int apply_constraints, 
     d.device            = device;
     d.segments          = seg.data();
     d.n_segments        = (int)seg.size();
+    d.vector_padding    = vector_padding;
     *out                = reinterpret_cast<mfhn_op>(op_create(d));
   });
 }
@@ -518,11 +542,14 @@ int mfhn_op_vmult_host_slot(mfhn_op h, void *dst_host, const void *src_host, voi
     Operator &op = *reinterpret_cast<Operator *>(h);
     CUDA_CHECK(cudaSetDevice(op.device));
     cudaStream_t st    = static_cast<cudaStream_t>(stream);
-    const size_t bytes = (size_t)(op.n_owned + op.n_ghost) * (op.number == MFHN_F64 ? 8 : 4);
+    const size_t es = op.number == MFHN_F64 ? 8 : 4, bytes = (size_t)(op.n_owned + op.n_ghost) * es;
     if (!op.d_stage_src[slot])
       {
-        CUDA_CHECK(cudaMalloc(&op.d_stage_src[slot], std::max<size_t>(bytes, 8)));
-        CUDA_CHECK(cudaMalloc(&op.d_stage_dst[slot], std::max<size_t>(bytes, 8)));
+        const size_t padded = std::max<size_t>(bytes, 8) + (size_t)op.vector_padding * es;
+        CUDA_CHECK(cudaMalloc(&op.d_stage_src[slot], padded));
+        CUDA_CHECK(cudaMalloc(&op.d_stage_dst[slot], padded));
+        CUDA_CHECK(cudaMemset(op.d_stage_src[slot], 0, padded));
+        CUDA_CHECK(cudaMemset(op.d_stage_dst[slot], 0, padded));
       }
     CUDA_CHECK(cudaMemcpyAsync(op.d_stage_src[slot], src_host, bytes, cudaMemcpyHostToDevice, st));
     if (zero_dst)
@@ -738,6 +765,151 @@ int mfhn_dist_vmult(mfhn_dist h, void *dst, const void *src, void *stream, int z
 }
 int64_t mfhn_dist_launch_count(mfhn_dist h) { return h ? reinterpret_cast<Dist *>(h)->launches : 0; }
 
+// ---- CG with point-Jacobi (extension, BASELINE.json config 5) ---------------------------------------------------
+int mfhn_op_inverse_diagonal(mfhn_op h, mfhn_dist dh, void *inv_diag, void *stream)
+{
+  return guard([&] {
+    if (!h || !inv_diag) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t s  = op.number == MFHN_F64 ? 8 : 4;
+    CUDA_CHECK(cudaMemsetAsync(inv_diag, 0, (size_t)(op.n_owned + op.n_ghost) * s, st));
+    if (int rc = mfhn_op_diagonal(h, inv_diag, stream)) throw CudaError(mfhn_last_error() + std::string(" (status ") + std::to_string(rc) + ")");
+    if (dh)
+      {
+        // compress(add) of the ghost contributions: the exchange of a vmult with no cells
+        Dist &d       = *reinterpret_cast<Dist *>(dh);
+        NcclApi &nccl = NcclApi::get();
+        char *db      = static_cast<char *>(inv_diag);
+        NCCL_CHECK(nccl.GroupStart());
+        for (size_t i = 0; i < d.import_peers.size(); ++i)
+          NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
+                               d.import_peers[i], d.comm, st));
+        for (size_t i = 0; i < d.ghost_peers.size(); ++i)
+          NCCL_CHECK(nccl.Send(db + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0, d.ghost_peers[i], d.comm, st));
+        NCCL_CHECK(nccl.GroupEnd());
+        run_unpack_add(op.number, inv_diag, d.d_recv, d.d_import_idx, d.n_import, true, st);
+        if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(db + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, st));
+      }
+    run_invert_diagonal(op.number, inv_diag, op.n_owned, st);
+  });
+}
+
+int mfhn_cg_solve(mfhn_op h, mfhn_dist dh, void *x, const void *b, const void *inv_diag, const mfhn_cg_options *options, mfhn_cg_result *result,
+                  double *residual_history, void *stream)
+{
+  return guard([&] {
+    if (!h || !x || !b || !options) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    Dist *d      = reinterpret_cast<Dist *>(dh);
+    if (d && d->op != &op) throw InvalidArgument("the partitioned operator belongs to another operator");
+    if (options->max_iter < 1 || options->check_every < 1) throw InvalidArgument("max_iter and check_every must be positive");
+    CUDA_CHECK(cudaSetDevice(op.device));
+    cudaStream_t st    = static_cast<cudaStream_t>(stream);
+    const size_t es    = op.number == MFHN_F64 ? 8 : 4;
+    const long long n  = op.n_owned, nvec = op.n_owned + op.n_ghost;
+    const size_t bytes = (size_t)(nvec + op.vector_padding) * es;
+    const int max_iter = options->max_iter;
+    // work vectors r, u, w, p, s; scalars and residual history on the device
+    char *work = nullptr;
+    CUDA_CHECK(cudaMalloc(&work, 5 * bytes + cg_scalars_bytes() + sizeof(double) * (size_t)(max_iter + 1) + 64));
+    struct Free
+    {
+      char *p;
+      ~Free() { cudaFree(p); }
+    } guard_work{work};
+    CUDA_CHECK(cudaMemsetAsync(work, 0, 5 * bytes + cg_scalars_bytes() + sizeof(double) * (size_t)(max_iter + 1) + 64, st));
+    void *r = work, *u = work + bytes, *w = work + 2 * bytes, *p = work + 3 * bytes, *s = work + 4 * bytes;
+    void *sc      = work + 5 * bytes;
+    double *hist  = reinterpret_cast<double *>(work + 5 * bytes + ((cg_scalars_bytes() + 15) / 16) * 16);
+    const bool timed = options->timings != 0;
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() {
+      if (!timed) return;
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      CUDA_CHECK(cudaEventRecord(e, st));
+      ev.push_back(e);
+    };
+    auto apply = [&](void *dst, const void *src) {
+      if (d)
+        dist_vmult(*d, dst, src, st, 1);
+      else
+        {
+          CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)nvec * es, st));
+          op_vmult_range(op, dst, src, st, 0, op.n_cells);
+        }
+    };
+    auto reduce = [&]() {
+      if (!d) return;
+      // one batched all-reduce of (r.u, w.u, r.r) per iteration
+      NCCL_CHECK(NcclApi::get().AllReduce(sc, sc, 3, 8 /*ncclFloat64*/, 0 /*ncclSum*/, d->comm, st));
+    };
+    apply(r, x);
+    run_cg_residual(op.number, r, u, b, inv_diag, n, st);
+    mark(); // [0]
+    apply(w, u);
+    mark();
+    run_cg_dots(op.number, r, u, w, n, sc, st);
+    mark();
+    reduce();
+    mark();
+    run_cg_scalars(sc, hist, st);
+    double r0 = 0, res = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&r0, hist, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    int it = 0;
+    res    = r0;
+    // per iteration four marks: after update, vmult, dots, all-reduce
+    while (it < max_iter && r0 > 0.0)
+      {
+        run_cg_update(op.number, p, s, x, r, u, w, inv_diag, n, sc, st);
+        mark();
+        apply(w, u);
+        mark();
+        run_cg_dots(op.number, r, u, w, n, sc, st);
+        mark();
+        reduce();
+        mark();
+        run_cg_scalars(sc, hist, st);
+        ++it;
+        if (it % options->check_every == 0 || it == max_iter)
+          {
+            CUDA_CHECK(cudaMemcpyAsync(&res, hist + it, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (res <= options->rel_tol * r0) break;
+          }
+      }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (residual_history) CUDA_CHECK(cudaMemcpy(residual_history, hist, sizeof(double) * (size_t)(it + 1), cudaMemcpyDeviceToHost));
+    if (result)
+      {
+        result->iterations       = it;
+        result->initial_residual = r0;
+        result->final_residual   = res;
+        result->ms_vmult = result->ms_vector_ops = result->ms_allreduce = result->ms_total = 0;
+        if (timed && ev.size() >= 4)
+          {
+            auto ms = [&](size_t a, size_t b2) {
+              float t = 0;
+              cudaEventElapsedTime(&t, ev[a], ev[b2]);
+              return (double)t;
+            };
+            // marks: 0 residual | 1 vmult | 2 dots | 3 all-reduce | then per iteration: update, vmult, dots, all-reduce
+            for (size_t i = 4; i + 3 < ev.size(); i += 4)
+              {
+                result->ms_vector_ops += ms(i - 1, i) + ms(i + 1, i + 2); // scalars + update, dots
+                result->ms_vmult += ms(i, i + 1);
+                result->ms_allreduce += ms(i + 2, i + 3);
+              }
+            result->ms_total = ms(3, ev.size() - 1);
+          }
+      }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  });
+}
+
 int mfhn_vec_alloc(int64_t bytes, void **ptr)
 {
   return guard([&] {
@@ -778,8 +950,7 @@ int mfhn_dist_enable_peer(mfhn_dist h, void *src_local, void *dst_local, void *c
     if (!h || !src_local || !dst_local || !peer_src || !peer_dst) throw InvalidArgument("null argument");
     Dist &d      = *reinterpret_cast<Dist *>(h);
     Operator &op = *d.op;
-    if (!plane_supported(op.degree + 1) || op.geometry_type != MFHN_GEOM_CARTESIAN)
-      throw NotImplemented("peer mode covers the register-tiled plane kernel (Cartesian cells, degree <= 5)");
+    if (op.geometry_type != MFHN_GEOM_CARTESIAN) throw NotImplemented("peer mode covers Cartesian cells");
     CUDA_CHECK(cudaSetDevice(op.device));
     const size_t s = op.number == MFHN_F64 ? 8 : 4;
     std::vector<void *> gs((size_t)std::max<long long>(op.n_ghost, 1)), gd(gs.size());
@@ -802,6 +973,23 @@ int mfhn_dist_enable_peer(mfhn_dist h, void *src_local, void *dst_local, void *c
       }
     d.peer_src_local = src_local;
     d.peer_dst_local = dst_local;
+  });
+}
+int mfhn_dist_enable_peer_flags(mfhn_dist h, void *flags_local, void *const *peer_flags)
+{
+  return guard([&] {
+    if (!h || !flags_local || !peer_flags) throw InvalidArgument("null argument");
+    Dist &d = *reinterpret_cast<Dist *>(h);
+    CUDA_CHECK(cudaSetDevice(d.op->device));
+    std::vector<unsigned *> pf((size_t)d.world, nullptr);
+    for (int r = 0; r < d.world; ++r)
+      {
+        if (r != d.rank && !peer_flags[r]) throw InvalidArgument("flag arrays of all peers are required");
+        pf[r] = static_cast<unsigned *>(r == d.rank ? flags_local : peer_flags[r]);
+      }
+    cudaFree(d.d_peer_flags);
+    d.d_peer_flags = to_device(pf);
+    d.flags_local  = static_cast<unsigned *>(flags_local);
   });
 }
 int mfhn_dist_vmult_peer(mfhn_dist h, void *stream, int zero_dst)

@@ -26,21 +26,21 @@ class DeviceVector:
     """Device vector allocated by the library (cudaMalloc) so that it can be exported to the other
     ranks with CUDA IPC; exposes __cuda_array_interface__, `tensor` is a torch view of it."""
 
-    def __init__(self, n, dtype, device):
+    def __init__(self, n, dtype, device, padding=0):
         import ctypes as C
 
         import torch
 
-        self.n, self.itemsize = int(n), torch.empty(0, dtype=dtype).element_size()
+        self.n, self.itemsize, self.padding = int(n), torch.empty(0, dtype=dtype).element_size(), int(padding)
         self.typestr = "<f8" if self.itemsize == 8 else "<f4"
         p = C.c_void_p()
-        check(lib.mfhn_vec_alloc(self.n * self.itemsize, C.byref(p)))
+        check(lib.mfhn_vec_alloc((self.n + self.padding) * self.itemsize, C.byref(p)))  # zeroed
         self.ptr = p.value
-        self.tensor = torch.as_tensor(self, device=device)
+        self.tensor = torch.as_tensor(self, device=device)[:self.n]  # the spare entries stay behind the view
 
     @property
     def __cuda_array_interface__(self):
-        return {"shape": (self.n,), "typestr": self.typestr, "data": (self.ptr, False), "version": 2, "strides": None}
+        return {"shape": (self.n + self.padding,), "typestr": self.typestr, "data": (self.ptr, False), "version": 2, "strides": None}
 
     def ipc_handle(self):
         import torch
@@ -152,8 +152,8 @@ class GhostExchange:
             raise capi.MfhnError(1, "peer mode needs the native (NCCL) operator")
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         n = self.n_owned + self.n_ghost
-        self._peer_src_vec = DeviceVector(n, self.dtype, self.device)
-        self._peer_dst_vec = DeviceVector(n, self.dtype, self.device)
+        self._peer_src_vec = DeviceVector(n, self.dtype, self.device, padding=capi.VECTOR_PADDING)
+        self._peer_dst_vec = DeviceVector(n, self.dtype, self.device, padding=capi.VECTOR_PADDING)
         mine = torch.cat([self._peer_src_vec.ipc_handle(), self._peer_dst_vec.ipc_handle()]).to(self.device)
         allh = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine, group=self.group)
@@ -174,6 +174,24 @@ class GhostExchange:
         remote = np.ascontiguousarray(part.ghost_global - part.rank_begin[part.ghost_owner], dtype=np.int64) if part.n_ghost else np.zeros(0, np.int64)
         check(lib.mfhn_dist_enable_peer(self._native, self._peer_src_vec.ptr, self._peer_dst_vec.ptr, psrc, pdst,
                                         owner.ctypes.data_as(C.c_void_p), remote.ctypes.data_as(C.c_void_p)))
+        # barriers as flag exchanges in each other's memory (MFHN_PEER_BARRIER=nccl keeps the 4-byte all-reduces)
+        import os
+
+        self.peer_barrier = os.environ.get("MFHN_PEER_BARRIER", "flags")
+        if self.peer_barrier == "flags":
+            self._peer_flags_vec = DeviceVector(world + 4, torch.float32, self.device)  # (world + 1) x uint32, zeroed
+            mine = self._peer_flags_vec.ipc_handle().to(self.device)
+            allf = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allf, mine, group=self.group)
+            pflags = (C.c_void_p * world)()
+            for r in range(world):
+                if r == rank:
+                    continue
+                a = C.c_void_p()
+                check(lib.mfhn_ipc_open_handle(allf[r].cpu().contiguous().data_ptr(), C.byref(a)))
+                pflags[r] = a.value
+                self._peer_opened.append(a.value)
+            check(lib.mfhn_dist_enable_peer_flags(self._native, self._peer_flags_vec.ptr, pflags))
         dist.barrier(group=self.group)  # every rank has opened what it needs before anyone proceeds
         self.peer_src, self.peer_dst = self._peer_src_vec.tensor, self._peer_dst_vec.tensor
         return self.peer_dst, self.peer_src
@@ -288,6 +306,8 @@ class GhostExchange:
         per non-empty partition) plus the pack / unpack kernels of the exchange."""
         s0, s1, s2, s3 = self.seg
         cells = int(s1 > s0) + int(s2 > s1) + int(s3 > s2) if cell_launches is None else int(cell_launches)
+        if self._native is not None and getattr(self, "peer_src", None) is not None:
+            return cells + (2 if getattr(self, "peer_barrier", "nccl") == "flags" else 0)  # two barrier kernels
         if self._native is not None:
             return cells + 2 * int(self.part.n_import_indices() > 0)  # one pack + one unpack kernel
         return cells + 2 * len(self.import_peers)

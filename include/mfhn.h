@@ -182,12 +182,19 @@ typedef struct
                                   mfhn_op_vmult_range may only be called on unions of segments
                                   (deal.II's cell_loop partitions for communication overlap)   */
   int n_segments;
+  int vector_padding;          /* the caller promises that every src / dst vector has this many valid (zero, never
+                                  inspected) entries BEHIND its n_owned + n_ghost entries.  With >= 4 the bulk-copy
+                                  kernel may treat the block that ends the vector like any other (its 16-byte
+                                  widened range reaches past the last entry); 0 = such a cell runs separately */
 } mfhn_op_desc;
 
 int mfhn_op_create(const mfhn_op_desc *desc, mfhn_op *out);
 /* The operator of a MatrixFree handle (Cartesian cells, segments = its three cell partitions): what
  * LaplaceOperator's constructor does with matrix_free.reinit (benchmark_03.h:326-340). */
 int mfhn_op_create_mf(mfhn_mf m, int number, int kernel, int apply_constraints, int device, mfhn_op *out);
+/* Same with the vector_padding promise of mfhn_op_desc (vectors allocated with MFHN_VECTOR_PADDING spare entries). */
+#define MFHN_VECTOR_PADDING 4
+int mfhn_op_create_mf_padded(mfhn_mf m, int number, int kernel, int apply_constraints, int device, int vector_padding, mfhn_op *out);
 void mfhn_op_destroy(mfhn_op op);
 
 /* dst (+)= A src on device vectors of n_owned+n_ghost entries of the operator's
@@ -273,6 +280,8 @@ int mfhn_dist_create(mfhn_op op, const mfhn_dist_desc *desc, mfhn_dist *out);
 /* Same from a MatrixFree handle whose import lists are set. */
 int mfhn_dist_create_mf(mfhn_op op, mfhn_mf m, const void *unique_id, mfhn_dist *out);
 void mfhn_dist_destroy(mfhn_dist d);
+/* NOTE: the ghost section of src is scratch: it receives the imported entries and is cleared again
+ * (zero_out_ghost_values), so src is written although it is declared const. */
 int mfhn_dist_vmult(mfhn_dist d, void *dst, const void *src, void *cuda_stream, int zero_dst);
 int64_t mfhn_dist_launch_count(mfhn_dist d);
 
@@ -280,8 +289,8 @@ int64_t mfhn_dist_launch_count(mfhn_dist d);
  * the ghost entries from the OWNER's src and add their contributions into the OWNER's dst through
  * peer-mapped (CUDA IPC) pointers over NVLink -- no pack / unpack kernels, no data-path collective;
  * two 4-byte all-reduces act as barriers.  The vector pair must come from mfhn_vec_alloc so that it
- * can be exported; every rank passes the opened peer pointers of all ranks.  Register-tiled plane
- * kernel only (Cartesian cells, degree <= 5). */
+ * can be exported; every rank passes the opened peer pointers of all ranks.  The boundary cells run
+ * through the plane kernels (all degrees), the interior cells through the operator's own kernel. */
 int mfhn_vec_alloc(int64_t bytes, void **dev_ptr);
 int mfhn_vec_free(void *dev_ptr);
 int mfhn_ipc_get_handle(void *dev_ptr, void *handle64);
@@ -290,7 +299,38 @@ int mfhn_ipc_close_handle(void *dev_ptr);
 int mfhn_dist_enable_peer(mfhn_dist d, void *src_local, void *dst_local, void *const *peer_src,
                           void *const *peer_dst, const int32_t *ghost_owner,
                           const int64_t *ghost_remote_index);
+/* Optional: barriers of the peer path as flag exchanges in each other's memory instead of NCCL all-reduces.
+ * flags_local: at least (world + 1) * 4 zeroed bytes from mfhn_vec_alloc on this rank; peer_flags[r]: rank r's array
+ * opened with mfhn_ipc_open_handle (entry of the own rank ignored).  With flags the whole vmult consists of CUDA
+ * kernels, memsets and events only: it can be captured in a CUDA graph. */
+int mfhn_dist_enable_peer_flags(mfhn_dist d, void *flags_local, void *const *peer_flags);
 int mfhn_dist_vmult_peer(mfhn_dist d, void *cuda_stream, int zero_dst);
+
+/* ---------------------------------------------------------------------------
+ * Conjugate gradients with a point-Jacobi preconditioner (BASELINE.json config 5).  EXTENSION: the reference contains
+ * no solver; this is the step either side of vmult in a real solve -- vmult + fused vector updates + one batched
+ * dot-product all-reduce per iteration (Chronopoulos / Gear form), all on the device.
+ * ------------------------------------------------------------------------ */
+typedef struct
+{
+  int max_iter;
+  double rel_tol;  /* stop when |r| <= rel_tol |r_0| (checked every check_every iterations)                    */
+  int check_every; /* the host reads the residual only every so many iterations                                */
+  int timings;     /* != 0: split the device time of the iterations into vmult / vector kernels / all-reduce   */
+} mfhn_cg_options;
+typedef struct
+{
+  int iterations;
+  double initial_residual, final_residual;
+  double ms_total, ms_vmult, ms_vector_ops, ms_allreduce; /* device time of the iterations (timings != 0) */
+} mfhn_cg_result;
+/* inv_diag = 1 / diag(A) on the owned entries (0 where the diagonal vanishes: hanging entries); dist may be NULL. */
+int mfhn_op_inverse_diagonal(mfhn_op op, mfhn_dist dist, void *inv_diag, void *cuda_stream);
+/* Solves A x = b from the start vector x; b must be consistent (the Laplace operator without Dirichlet data is
+ * singular).  x, b, inv_diag: device vectors of the operator (inv_diag NULL = no preconditioner); dist NULL = one
+ * rank.  residual_history (host, max_iter + 1 doubles) may be NULL.  Synchronises the stream. */
+int mfhn_cg_solve(mfhn_op op, mfhn_dist dist, void *x, const void *b, const void *inv_diag, const mfhn_cg_options *options,
+                  mfhn_cg_result *result, double *residual_history, void *cuda_stream);
 
 /* Host-only check of the MFHN_KERNEL_BULK layout for a reference index array (read_dof_values order,
  * benchmark_03.h:255-258): n_irregular = cells that do not show contiguous cell-interior / face blocks

@@ -168,8 +168,9 @@ public:
     cudaFree(d_);
     d_ = nullptr;
     n_ = n;
-    if (cudaMalloc(&d_, sizeof(Number) * (n > 0 ? n : 1)) != cudaSuccess) throw ExcMessage("cudaMalloc failed");
-    *this = Number(0);
+    // MFHN_VECTOR_PADDING spare (zero) entries behind the vector: see mfhn_op_desc::vector_padding
+    if (cudaMalloc(&d_, sizeof(Number) * (n + MFHN_VECTOR_PADDING)) != cudaSuccess) throw ExcMessage("cudaMalloc failed");
+    cudaMemset(d_, 0, sizeof(Number) * (n + MFHN_VECTOR_PADDING));
   }
   Vector &operator=(Number v)
   {
@@ -209,7 +210,8 @@ public:
     : matrix_free_(matrix_free)
   {
     if (matrix_free.sizes().degree != fe_degree) throw ExcMessage("Degrees do not match!"); // benchmark_01.h:204-206
-    check(mfhn_op_create_mf(matrix_free.handle(), sizeof(Number) == 8 ? MFHN_F64 : MFHN_F32, kernel, apply_constraints, -1, &op_));
+    check(mfhn_op_create_mf_padded(matrix_free.handle(), sizeof(Number) == 8 ? MFHN_F64 : MFHN_F32, kernel, apply_constraints, -1,
+                                   MFHN_VECTOR_PADDING, &op_)); // Vector::reinit pads its allocation
   }
   ~LaplaceOperator()
   {

@@ -101,7 +101,7 @@ def test_bulk_kernel_ranges_irregular_cells_and_alignment(mfhn, k, number):
     y = dst.cpu().numpy().astype(np.float64)
     assert np.abs(y - ref).max() / np.abs(ref).max() < TOL[number]
     # unaligned views are rejected (bulk copies need 16-byte aligned addresses)
-    big = torch.zeros(src.numel() + 4, dtype=src.dtype, device=src.device)
+    big = torch.zeros(src.numel() + 8, dtype=src.dtype, device=src.device)
     with pytest.raises(mfhn.MfhnError):
         op.vmult(dst, big[1 : 1 + src.numel()])
     op.set_kernel("plane")
@@ -408,9 +408,16 @@ def test_diagonal_and_jacobi_cg(mfhn, geo, L, k):
     live = ~O1.is_hanging
     xs = np.zeros(lay.n_dofs)
     xs[live] = np.random.default_rng(5).uniform(-1, 1, live.sum())
-    b = torch.from_numpy(A @ xs).cuda()
+    b = op.initialize_dof_vector()
+    b.copy_(torch.from_numpy(A @ xs))
     x = op.initialize_dof_vector()
     its_jacobi, hist = mfhn.solve_cg(op, x, b, diag=diag, rel_tol=1e-10, max_iter=2000)
+    # the library's own inverse diagonal (mfhn_op_inverse_diagonal) and the device-time split
+    inv = mfhn.inverse_diagonal(op)
+    assert np.allclose(inv.cpu().numpy()[live], 1.0 / ref[live], rtol=1e-12) and (inv.cpu().numpy()[O1.is_hanging] == 0).all()
+    x3 = op.initialize_dof_vector()
+    its3, hist3, split = mfhn.solve_cg(op, x3, b, inverse=inv, rel_tol=1e-10, max_iter=2000, check_every=10, timings=True)
+    assert its_jacobi <= its3 <= its_jacobi + 10 and split["ms_vmult"] > 0 and split["ms_vector_ops"] > 0
     assert hist[-1] <= 1e-10 * hist[0] and its_jacobi < 2000
     xn = x.cpu().numpy()
     assert np.abs(A @ xn - A @ xs).max() <= 1e-8 * np.abs(A @ xs).max()
