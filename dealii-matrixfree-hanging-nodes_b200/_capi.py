@@ -127,6 +127,7 @@ SIGNATURES = {
     "mfhn_unpack_add": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mfhn_bench_dfma": (c_int, [c_int, c_int, P(c_double)]),
     "mfhn_bulk_layout_check": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, P(c_int64), P(c_int64)]),
+    "mfhn_runs_layout_check": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, P(c_int64), P(c_int64), P(c_int64), P(c_int64)]),
     "mfhn_dist_unique_id": (c_int, [c_void_p]),
     "mfhn_dist_create": (c_int, [c_void_p, P(DistDesc), P(c_void_p)]),
     "mfhn_dist_create_mf": (c_int, [c_void_p, c_void_p, c_void_p, P(c_void_p)]),
@@ -174,4 +175,4 @@ VECTOR_PADDING = 4  # MFHN_VECTOR_PADDING: spare entries behind every vector han
 SERIAL, P4EST = 0, 1
 GEOM_CARTESIAN, GEOM_AFFINE, GEOM_GENERAL = 0, 1, 2
 KERNEL_AUTO, KERNEL_QPOINT, KERNEL_SEPARABLE, KERNEL_BASELINE, KERNEL_PLANE, KERNEL_PATCH = 0, 1, 2, 3, 4, 5
-KERNELS = {"auto": 0, "qpoint": 1, "separable": 2, "baseline": 3, "plane": 4, "patch": 5, "bulk": 6}
+KERNELS = {"auto": 0, "qpoint": 1, "separable": 2, "baseline": 3, "plane": 4, "patch": 5, "bulk": 6, "runs": 7}

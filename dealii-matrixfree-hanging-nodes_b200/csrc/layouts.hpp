@@ -78,6 +78,37 @@ struct BulkLayout
   }
 };
 
+// run-wise layout of MFHN_KERNEL_RUNS (kernels_runs.cuh)
+struct RunsHostLayout
+{
+  int n = 0, E = 2, cap = 0, NT = 0, RW = 0, BR = 0, sr = 0;
+  long long n_cells = 0, n_batches = 0, n_blocks = 0, n_singles = 0, n_zero = 0;
+  std::vector<uint32_t> rec, srow, ov_idx; // rec: RW words per batch
+  std::vector<uint16_t> sprow, ov_pos, zpos;
+};
+
+struct RunsLayout
+{
+  int n = 0, sr = 0;
+  long long n_cells = 0, n_batches = 0, n_blocks = 0, n_singles = 0, n_zero = 0, staging_wavefronts = 0;
+  uint32_t *d_rec = nullptr, *d_srow = nullptr, *d_ov_idx = nullptr;
+  uint16_t *d_sprow = nullptr, *d_ov_pos = nullptr, *d_zpos = nullptr;
+  bool usable = false;
+
+  void free()
+  {
+    cudaFree(d_rec);
+    cudaFree(d_srow);
+    cudaFree(d_ov_idx);
+    cudaFree(d_sprow);
+    cudaFree(d_ov_pos);
+    cudaFree(d_zpos);
+    d_rec = d_srow = d_ov_idx = nullptr;
+    d_sprow = d_ov_pos = d_zpos = nullptr;
+    usable = false;
+  }
+};
+
 struct BaselineArrays
 {
   uint32_t *l2g = nullptr;
@@ -87,6 +118,7 @@ struct BaselineArrays
 constexpr bool plane_supported(int n) { return n >= 2 && n <= 6; }      // register-tiled plane kernel
 constexpr bool plane_smem_supported(int n) { return n >= 2 && n <= 9; } // plane in shared memory
 constexpr bool bulk_supported(int n) { return n >= 4 && n <= 6; }
+constexpr bool runs_supported(int n) { return n >= 2 && n <= 6; } // staging positions are bytes: (k+1)^3 <= 256
 
 // ---- launch entry points (degree = k, number = MFHN_F64 / MFHN_F32); they throw std::runtime_error ----
 // k_generic_*.cu
@@ -98,6 +130,10 @@ void run_plane(int degree, int number, const PlaneLayout &L, const CellLoopParam
 void run_bulk(int degree, int number, const BulkLayout &L, const CellLoopParams &p, int device, cudaStream_t stream);
 void bulk_analyze(BulkHostLayout &L, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx);
 long long bulk_verify(const BulkHostLayout &L, int number, const uint32_t *idx);
+// k_runs.cu
+void run_runs(int degree, int number, const RunsLayout &L, const CellLoopParams &p, int device, cudaStream_t stream);
+void runs_analyze(RunsHostLayout &L, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx, int max_gap, int min_run, bool place);
+long long runs_verify(const RunsHostLayout &L, int number, const uint32_t *idx, long long *staging_wavefronts);
 // k_misc.cu
 void run_baseline(int degree, int number, BaselineArrays &arrays, const uint32_t *d_idx, const void *d_h, long long n_cells, const CellLoopParams &p,
                   int device, cudaStream_t stream);

@@ -84,6 +84,35 @@ static void bulk_build(BulkLayout &B, int n, int number, long long n_cells, long
   B.d_cinfo = to_device(L.cinfo);
 }
 
+// ---- run-wise layout ------------------------------------------------------------------
+// run detection parameters (development switches MFHN_RUNS_GAP / MFHN_RUNS_MIN): unused vector entries tolerated
+// inside a run, fewest cell entries worth a bulk copy
+static int env_int(const char *name, int fallback)
+{
+  const char *e = std::getenv(name);
+  return e && *e ? std::atoi(e) : fallback;
+}
+static void runs_build(RunsLayout &B, int n, int number, long long n_cells, long long n_vec, const uint32_t *idx)
+{
+  RunsHostLayout L;
+  runs_analyze(L, n, number, n_cells, n_vec, idx, env_int("MFHN_RUNS_GAP", 10), env_int("MFHN_RUNS_MIN", 6), env_int("MFHN_RUNS_PLACE", 1) != 0);
+  B.n         = n;
+  B.sr        = L.sr;
+  B.n_cells   = n_cells;
+  B.n_batches = L.n_batches;
+  B.n_blocks  = L.n_blocks;
+  B.n_singles = L.n_singles;
+  B.n_zero    = L.n_zero;
+  if (env_int("MFHN_RUNS_STATS", 0)) runs_verify(L, number, idx, &B.staging_wavefronts);
+  B.d_rec     = to_device(L.rec);
+  B.d_srow    = to_device(L.srow);
+  B.d_sprow   = to_device(L.sprow);
+  B.d_ov_idx  = to_device(L.ov_idx);
+  B.d_ov_pos  = to_device(L.ov_pos);
+  B.d_zpos    = to_device(L.zpos);
+  B.usable    = true;
+}
+
 struct Operator
 {
   int degree = 0, number = 0, device = 0, geometry_type = 0;
@@ -94,6 +123,7 @@ struct Operator
   void *d_geom = nullptr;       // Number h[cell], Number G[cell][6] or Number G[cell][6][q]
   PlaneLayout plane;            // warp-interleaved layout of the plane kernels
   BulkLayout bulk;              // block descriptors of the bulk-copy kernel (degrees 3..5)
+  RunsLayout runs;              // run descriptors of the run-wise bulk-copy kernel (degrees 1..5)
   BaselineArrays baseline;      // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use)
   std::vector<long long> segments;
   long long launches = 0;
@@ -115,6 +145,7 @@ struct Operator
     cudaFree(baseline.jxw);
     plane.free();
     bulk.free();
+    runs.free();
   }
 };
 
@@ -173,6 +204,28 @@ void launch_kernel(Operator &op, int kernel, const CellLoopParams &p, cudaStream
       for (const long long c : op.bulk.irregular)
         if (c >= b0 && c < std::min(b1, p.cell_end)) plane_part(c, c + 1);
     }
+  else if (kernel == MFHN_KERNEL_RUNS)
+    {
+      // whole warp batches; the (at most cpw - 1) cells in front of an unaligned range go to the plane kernel
+      const long long cpw = 32 / (op.degree + 1);
+      const long long b0  = std::min((p.cell_begin + cpw - 1) / cpw * cpw, p.cell_end);
+      const long long b1  = p.cell_end == op.n_cells ? p.cell_end : std::max(b0, p.cell_end / cpw * cpw);
+      auto part = [&](const long long cb, const long long ce, const bool runs) {
+        if (ce <= cb) return;
+        CellLoopParams q = p;
+        q.cell_begin     = cb;
+        q.cell_end       = ce;
+        if (runs)
+          run_runs(op.degree, op.number, op.runs, q, op.device, stream);
+        else
+          run_plane(op.degree, op.number, op.plane, q, op.device, stream, nullptr);
+        ++op.launches;
+      };
+      part(p.cell_begin, b0, false);
+      part(b0, b1, true);
+      part(b1, p.cell_end, false);
+      return;
+    }
   else if (kernel == MFHN_KERNEL_PLANE)
     run_plane(op.degree, op.number, op.plane, p, op.device, stream, nullptr);
   else
@@ -195,9 +248,10 @@ int resolve_kernel(const Operator &op)
   if (kernel == MFHN_KERNEL_BULK && !bulk_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
   if (kernel == MFHN_KERNEL_BULK && op.geometry_type == MFHN_GEOM_CARTESIAN && !op.bulk.usable)
     throw InvalidArgument("MFHN_KERNEL_BULK: the DoF numbering does not show contiguous cell-interior / face blocks");
+  if (kernel == MFHN_KERNEL_RUNS && (!runs_supported(op.degree + 1) || !op.runs.usable)) throw NotImplemented("MFHN_KERNEL_RUNS is available for degrees 1..5");
   if (kernel == MFHN_KERNEL_PATCH)
     throw NotImplemented("MFHN_KERNEL_PATCH (sorted-unique patch gather, round 1) was measured slower than the plane kernel and has been removed");
-  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
+  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_RUNS || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
   if (kernel == MFHN_KERNEL_BASELINE && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("the baseline kernel is set up for Cartesian cells");
@@ -218,10 +272,10 @@ void op_vmult_range(Operator &op, void *dst, const void *src, cudaStream_t strea
   p.cell_end          = ce;
   p.apply_constraints = op.apply_constraints;
   int kernel          = resolve_kernel(op);
-  if (kernel == MFHN_KERNEL_BULK && (((uintptr_t)src | (uintptr_t)dst) & 15u))
+  if ((kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_RUNS) && (((uintptr_t)src | (uintptr_t)dst) & 15u))
     {
       if (op.kernel != MFHN_KERNEL_AUTO)
-        throw InvalidArgument("MFHN_KERNEL_BULK needs 16-byte aligned vectors (use MFHN_KERNEL_PLANE for unaligned views)");
+        throw InvalidArgument("MFHN_KERNEL_BULK / MFHN_KERNEL_RUNS need 16-byte aligned vectors (use MFHN_KERNEL_PLANE for unaligned views)");
       kernel = MFHN_KERNEL_PLANE; // AUTO: unaligned views take the plane kernel
     }
   launch_kernel(op, kernel, p, stream);
@@ -235,7 +289,7 @@ Operator *op_create(const mfhn_op_desc &d)
   if (d.n_cells > 0 && (!d.dof_indices || !d.masks || !d.geometry)) throw InvalidArgument("null array");
   if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE && d.geometry_type != MFHN_GEOM_GENERAL)
     throw InvalidArgument("unknown geometry type");
-  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_BULK) throw InvalidArgument("unknown kernel");
+  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_RUNS) throw InvalidArgument("unknown kernel");
   int device = d.device;
   if (device < 0)
     CUDA_CHECK(cudaGetDevice(&device));
@@ -311,6 +365,7 @@ Operator *op_create(const mfhn_op_desc &d)
       if (d.vector_padding < 0) throw InvalidArgument("negative vector padding");
       op->vector_padding = d.vector_padding;
       if (bulk_supported(n)) bulk_build(op->bulk, n, d.number, d.n_cells, nvec + d.vector_padding, d.dof_indices);
+      if (runs_supported(n)) runs_build(op->runs, n, d.number, d.n_cells, nvec + d.vector_padding, d.dof_indices);
     }
   resolve_kernel(*op);
   return op.release();
@@ -595,7 +650,7 @@ int mfhn_op_set_kernel(mfhn_op h, int kernel)
     if (!h) throw InvalidArgument("null argument");
     Operator &op  = *reinterpret_cast<Operator *>(h);
     const int old = op.kernel;
-    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_BULK) throw InvalidArgument("unknown kernel");
+    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_RUNS) throw InvalidArgument("unknown kernel");
     op.kernel = kernel;
     try
       {
@@ -638,6 +693,16 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
       *value = (double)op.n_cells * (12 * n * n * (n * n + 2 * n) + 3 * n3);
     else if (w == "kernel")
       *value = (double)resolve_kernel(op);
+    else if (w == "runs_bulk_copies") // bulk copies / single entries / zeroed entries of the run-wise layout, whole mesh
+      *value = op.runs.usable ? (double)op.runs.n_blocks : -1.0;
+    else if (w == "runs_single_entries")
+      *value = op.runs.usable ? (double)op.runs.n_singles : -1.0;
+    else if (w == "runs_zero_entries")
+      *value = op.runs.usable ? (double)op.runs.n_zero : -1.0;
+    else if (w == "runs_single_rounds") // rounds of the fixed-stride single-entry rows
+      *value = op.runs.usable ? (double)op.runs.sr : -1.0;
+    else if (w == "runs_staging_wavefronts") // bank model of the staging reads (MFHN_RUNS_STATS=1 at creation), 2 per plane slot and batch = no conflict
+      *value = (double)op.runs.staging_wavefronts;
     else if (w == "bulk_irregular_cells") // cells the bulk-copy kernel leaves to the plane kernel (-1: layout not usable)
       *value = op.bulk.usable ? (double)op.bulk.irregular.size() : -1.0;
     else
@@ -656,6 +721,24 @@ int mfhn_bulk_layout_check(int degree, int number, int64_t n_cells, int64_t n_ve
     bulk_analyze(L, degree + 1, number, n_cells, n_vec, dof_indices);
     if (n_irregular) *n_irregular = (int64_t)L.irregular.size();
     if (n_mismatch) *n_mismatch = bulk_verify(L, number, dof_indices);
+  });
+}
+
+int mfhn_runs_layout_check(int degree, int number, int64_t n_cells, int64_t n_vec, const uint32_t *dof_indices, int max_gap, int min_run, int place,
+                           int64_t *n_bulk_copies, int64_t *n_single_entries, int64_t *n_mismatch, int64_t *staging_wavefronts)
+{
+  return guard([&] {
+    if (n_cells > 0 && !dof_indices) throw InvalidArgument("null argument");
+    if (number != MFHN_F64 && number != MFHN_F32) throw InvalidArgument("number must be MFHN_F64 or MFHN_F32");
+    if (max_gap < 0 || min_run < 1) throw InvalidArgument("max_gap must be >= 0 and min_run >= 1");
+    RunsHostLayout L;
+    runs_analyze(L, degree + 1, number, n_cells, n_vec, dof_indices, max_gap, min_run, place != 0);
+    if (n_bulk_copies) *n_bulk_copies = L.n_blocks;
+    if (n_single_entries) *n_single_entries = L.n_singles;
+    long long wf = 0;
+    const long long bad = runs_verify(L, number, dof_indices, &wf);
+    if (n_mismatch) *n_mismatch = bad;
+    if (staging_wavefronts) *staging_wavefronts = wf;
   });
 }
 

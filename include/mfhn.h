@@ -54,6 +54,9 @@ typedef struct mfhn_op_s *mfhn_op;
 #define MFHN_KERNEL_PATCH 5     /* removed (round-1 experiment: sorted-unique patch gather, slower than PLANE); returns MFHN_ERR_NOT_IMPL */
 #define MFHN_KERNEL_BULK 6      /* plane kernel; cell-interior and face blocks moved by the bulk-copy engine
                                    (cp.async.bulk / cp.reduce.async.bulk), degrees 3..5, 16-byte aligned vectors */
+#define MFHN_KERNEL_RUNS 7      /* plane kernel; every cell's vector entries cut into contiguous runs at setup (any
+                                   numbering), long runs moved by the bulk-copy engine, the rest entry by entry;
+                                   degrees 1..5, 16-byte aligned vectors */
 
 const char *mfhn_last_error(void);
 const char *mfhn_version(void);
@@ -338,6 +341,15 @@ int mfhn_cg_solve(mfhn_op op, mfhn_dist dist, void *x, const void *b, const void
  * wrong (must be 0).  Needs no GPU. */
 int mfhn_bulk_layout_check(int degree, int number, int64_t n_cells, int64_t n_vec, const uint32_t *dof_indices,
                            int64_t *n_irregular, int64_t *n_mismatch);
+
+/* Host-only check of the MFHN_KERNEL_RUNS layout: runs of the sorted per-cell index lists with at most max_gap unused
+ * entries inside and at least min_run cell entries become bulk copies, the rest single entries; place != 0 chooses
+ * the staging positions against shared-memory bank conflicts.  n_mismatch = entries an emulated gather gets wrong +
+ * copied foreign entries that would not be zero in the scatter (must be 0); staging_wavefronts = bank model of the
+ * staging reads, summed over the warp batches (2 per plane slot = conflict-free). */
+int mfhn_runs_layout_check(int degree, int number, int64_t n_cells, int64_t n_vec, const uint32_t *dof_indices, int max_gap,
+                           int min_run, int place, int64_t *n_bulk_copies, int64_t *n_single_entries, int64_t *n_mismatch,
+                           int64_t *staging_wavefronts);
 
 /* Microbenchmarks used for the roofline denominators (bench.py). */
 int mfhn_bench_dfma(int number, int iters, double *tflops);
