@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                     help="partitioned runs: NCCL ghost import/compress (default) or peer-memory access of the owners' vectors")
     ap.add_argument("--hn-weight", type=float, default=1.0, help="partition weight of cells with hanging nodes (benchmark_02.cc:15-37)")
-    ap.add_argument("--sweep", action="store_true", help="also time degrees 1..8 and the kernel variants (extra keys)")
+    ap.add_argument("--sweep", action="store_true", help="degree sweep with L=10 for k=1,2 and all kernel variants (the default line carries the compact sweep)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the compact degree sweep (degrees 1..8, double + float) of the default line")
+    ap.add_argument("--no-weak", action="store_true", help="8 GPUs: skip the extra weak-scaling run on the next finer mesh")
     ap.add_argument("--stages", action="store_true", help="the reference's DG (SC) / CG (SC) decomposition and eta (benchmark_01.cc:189-220)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -113,17 +115,10 @@ class ClockSampler:
 
 
 def default_refinements(args):
+    """The same mesh at every N (strong scaling): SURVEY 8d / BASELINE.md C2: annulus (p4est flavour) L=9 for k <= 4
+    (142.8 M DoFs at k=4), L=8 for k >= 5.  The 8-GPU weak-scaling run on L+1 is an extra key of the N=8 line."""
     if args.refinements is not None:
         return args.refinements
-    if args.geometry == "annulus" and args.degree == 4 and int(os.environ.get("WORLD_SIZE", "1")) == 8:
-        return 10  # weak scaling: 1.124 B DoFs on 8 GPUs = 140.5 M per GPU (N=1: 142.8 M)
-    # SURVEY 8d / BASELINE.md C2: annulus (p4est flavour) L=9 for k <= 4 (142.8 M DoFs at k=4), L=8 for k >= 5
-    if args.geometry == "annulus":
-        return 9 if args.degree <= 4 else 8
-    return 8 if args.degree <= 4 else 7
-
-
-def default_refinements_single(args):
     if args.geometry == "annulus":
         return 9 if args.degree <= 4 else 8
     return 8 if args.degree <= 4 else 7
@@ -155,26 +150,41 @@ def time_vmult(torch, op, dst, src, steps, warmup, barrier=None, graph=None):
     return ev[0].elapsed_time(ev[steps]), per
 
 
-def cpu_sample(mf, n_sample_cells):
-    """Bounded sample of the workload for the CPU arm: the first cells along the
-    Morton curve with their DoFs renumbered compactly."""
+def cpu_sample(mf, n_sample_cells, n_windows=100):
+    """Bounded sample of the workload for the CPU arm: n_windows windows of consecutive cells, evenly spaced over the
+    whole cell loop (Morton order), so that the sample's share of cells with hanging nodes matches the mesh's; the
+    DoFs of the sample are renumbered compactly."""
     ns = min(n_sample_cells, mf.n_cells)
-    idx = mf.dof_indices[:ns]
+    w = max(ns // n_windows, 1)
+    starts = np.linspace(0, mf.n_cells - w, num=max(ns // w, 1)).astype(np.int64)
+    cells = np.unique((starts[:, None] + np.arange(w)[None, :]).reshape(-1))
+    idx = mf.dof_indices[cells]
     uniq, inv = np.unique(idx, return_inverse=True)
-    return inv.reshape(idx.shape).astype(np.uint32), mf.masks[:ns], mf.h[:ns], len(uniq), ns
+    masks = np.ascontiguousarray(mf.masks[cells])
+    return inv.reshape(idx.shape).astype(np.uint32), masks, np.ascontiguousarray(mf.h[cells]), len(uniq), len(cells), int((masks != 0).sum())
 
 
-def run_cpu(args, mf, degree, n_rep, n_sample_cells=200_000, threads=None):
+def run_cpu(args, mf, degree, n_rep, n_sample_cells=200_000, threads=None, warmup=1):
     from oracle import cpu
 
     threads = threads or os.cpu_count()
-    idx, masks, h, nd, ns = cpu_sample(mf, n_sample_cells)
-    cpu.benchmark(degree, idx, masks, h, nd, True, 1, threads)  # spin up the thread pool
+    idx, masks, h, nd, ns, ns_hn = cpu_sample(mf, n_sample_cells)
+    for _ in range(max(warmup, 1)):
+        cpu.benchmark(degree, idx, masks, h, nd, True, 1, threads)  # spin up the thread pool
     t = cpu.benchmark(degree, idx, masks, h, nd, True, n_rep, threads)
-    return {"value": threads * nd / t / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {ns} cells of the Morton curve ({nd} DoFs) of the same mesh, src=1, {n_rep} reps per thread, "
-                      f"every thread applies the operator to its own vectors (benchmark_01.h:536-573); "
-                      f"C restatement of the deal.II CPU path (AVX-512 across 8 cells, even-odd sum factorisation), not deal.II"}, t, nd
+    return {"value": threads * nd / t / 1e9, "unit": UNIT, "cores": threads, "kind": "port", "sample_n_cells": ns, "sample_n_cells_hn": ns_hn,
+            "sample_hn_fraction": ns_hn / max(ns, 1), "mesh_hn_fraction": mf.n_cells_hn() / max(mf.n_cells, 1),
+            "sample": f"{ns} cells ({ns_hn} with hanging nodes, {nd} DoFs) of the same mesh: 100 windows of consecutive cells evenly spaced over the "
+                      f"Morton-ordered cell loop, src=1, {n_rep} reps per thread; every thread applies the operator to its own vectors "
+                      f"(benchmark_01.h:536-573); C restatement of the deal.II CPU path (AVX-512 across 8 cells, even-odd sum factorisation); "
+                      f"deal.II itself cannot be built here"}, t, nd
+
+
+def problem_config(args, workload, tria, n_dofs, world):
+    """Workload description shared by both arms (the reference arm prints the same object)."""
+    return {"workload": workload, "n_cells": int(tria.n_active_cells()), "n_cells_hn": int(tria.n_cells_with_hanging_nodes()), "n_dofs": int(n_dofs),
+            "l2": "inputs larger than L2 (vectors + index arrays >> 126 MB), no flush", "dst": "accumulating vmult like benchmark_03.h:352",
+            "exchange": args.exchange if world > 1 else None}
 
 
 def main():
@@ -205,22 +215,14 @@ def run():
         tria = mfhn.Triangulation(args.geometry, L, "p4est")
         dh = mfhn.DoFHandler(tria, args.degree)
         mf = mfhn.MatrixFree(dh)
-        from oracle import cpu
-
-        threads = os.cpu_count()
-        idx, masks, h, nd, ns = cpu_sample(mf, 200_000)
-        for _ in range(max(args.warmup, 0)):
-            cpu.benchmark(args.degree, idx, masks, h, nd, True, 1, threads)
         t0 = time.perf_counter()
-        t = cpu.benchmark(args.degree, idx, masks, h, nd, True, args.steps, threads)
+        cb, t, nd = run_cpu(args, mf, args.degree, args.steps, warmup=args.warmup)
         wall = time.perf_counter() - t0
-        v = threads * nd / t / 1e9
-        cb = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-              "sample": f"first {ns} cells of the Morton curve ({nd} DoFs per replica) of the same mesh; every thread applies the operator "
-                        f"to its own vectors (benchmark_01.h:536-573); C restatement of the deal.II CPU path (deal.II itself cannot be built here)"}
+        v = cb["value"]
         return json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "n_dofs": dh.n_dofs()},
+                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+                          "vs_baseline": None, "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic",
+                          "config": problem_config(args, workload, tria, dh.n_dofs(), args.gpus),
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "wall_s": wall})
 
@@ -276,28 +278,17 @@ def run():
         dst.zero_()
     ms_per_step = total_ms / args.steps
     value = n_dofs_global / (ms_per_step * 1e-3) / 1e9
+    parity = None
     if world > 1:
-        # the partitioned operator must keep constants in its null space (exercises both ghost exchanges)
-        if args.exchange == "peer":  # the check must run on the registered pair to exercise the peer path
-            keep = src.clone()
-            src.fill_(1.0)
-            op.vmult(dst, src, zero_dst=True)
-            worst = dst[:op.n_owned].abs().max().reshape(1).to(torch.float64)
-            src.copy_(keep)
-            dist.barrier()
-            dst.zero_()
-            del keep
-        else:
-            ones, chk = op.initialize_dof_vector(), op.initialize_dof_vector()
-            ones.fill_(1.0)
-            op.vmult(chk, ones)
-            worst = chk.abs().max().reshape(1).to(torch.float64)
-            del ones, chk
-        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        assert float(worst.item()) < 1e-9, f"distributed vmult failed A*1 = 0: {float(worst.item())}"
+        # partitioned vmult against the one-GPU operator on a small mesh, non-constant vector, both exchanges
+        from bench_dist import parity_check
+
+        parity = parity_check(mfhn, torch, dist, args, rank, world, src.device)
+        tol = 1e-12 if args.number == "double" else 1e-5
+        assert parity["nccl"] < tol and parity["peer"] < tol, f"partitioned vmult differs from the one-GPU operator: {parity}"
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 or L != default_refinements_single(args) else "strong", "vs_baseline": None,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
            "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic"}
     # kernels per step, counted by the engine itself: cell kernels of one vmult (the bulk-copy kernel adds a
     # plane-kernel launch for every cell it leaves out), plus pack / unpack in partitioned runs
@@ -307,6 +298,8 @@ def run():
     cell_launches = op.launch_count() - c0
     launches_per_step = cell_launches if world == 1 else prob["comm"].launches_per_vmult(cell_launches)
     out["gpu_launches"] = int(launches_per_step * args.steps)
+    if parity is not None:
+        out["parity_max_rel_err"] = parity
 
     # roofline of the dominant kernel (the fused cell kernel): algorithmic bytes / average launch time
     peak, peak_src = peaks()
@@ -321,12 +314,19 @@ def run():
     kernel_ms = float(np.mean(per)) if world == 1 else ms_per_step
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
     peak = peak * world  # aggregate over the GPUs of the job
-    traffic = None
+    # DRAM bytes per launch of this kernel from its ncu capture (profiles/traffic.json names the capture and the
+    # commit of the kernel source it was taken from; null when this configuration has no capture)
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{args.geometry}_L{L}_k{args.degree}_{args.number}_{prob['kernel_name']}")
-    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            tj = json.load(f)
+        entry = tj.get(f"{args.geometry}_L{L}_k{args.degree}_{args.number}_{prob['kernel_name']}")
+        if isinstance(entry, dict):
+            traffic, traffic_src = entry.get("bytes"), entry.get("source")
+        else:
+            traffic = entry
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "algorithmic_bytes_without_dst_read": b_alg_plain,
                        "bytes_note": "3 s n_dofs + n_cells (4 (k+1)^3 + 1 + 3 s): src read, dst read+write (accumulating vmult), uint32 indices, mask, Cartesian geometry",
                        "kernel_ms_min_avg_max": [float(per.min()), float(per.mean()), float(per.max())],
@@ -334,11 +334,8 @@ def run():
     out["clocks"] = clocks.summary()
     if rank_info is not None:
         out["ranks"] = rank_info
-    out["config"] = {"workload": workload, "n_cells": int(prob["n_cells_global"]), "n_cells_hn": int(prob["n_cells_hn_global"]),
-                     "n_dofs": int(n_dofs_global), "kernel": prob["kernel_name"], "partition": prob["partition"],
-                     "l2": "inputs larger than L2 (vectors + index arrays >> 126 MB), no flush",
-                     "dst": "accumulating vmult like benchmark_03.h:352", "setup_s": round(t_setup, 1),
-                     "exchange": args.exchange if world > 1 else None,
+    out["config"] = problem_config(args, workload, prob["tria"], n_dofs_global, world)
+    out["engine"] = {"kernel": prob["kernel_name"], "partition": prob["partition"], "setup_s": round(t_setup, 1),
                      "launch": "CUDA graph replay of one partitioned vmult" if graph is not None else "host launches"}
 
     if rank == 0 and world == 1 and not args.minimal:
@@ -354,7 +351,7 @@ def run():
         out["eta5"] = max((t_hn / (t_n / n_all) - (n_all - n_hn)) / n_hn, 1.0) if n_hn else 1.0
         # the other kernels on the same problem, for the record
         variants = {}
-        for kname in ("plane", "bulk", "qpoint", "separable", "baseline"):
+        for kname in ("plane", "bulk", "runs", "qpoint", "separable", "baseline"):
             try:
                 op.set_kernel(kname)
                 _, pk = time_vmult(torch, op, dst, src, 10, 3)
@@ -379,45 +376,76 @@ def run():
         del op_plain, mf_plain
 
     if not args.no_e2e and not args.minimal:
-        # end to end through the host-vector entry point: H2D of src, kernel, D2H of dst every step
+        # end to end with HOST vectors: H2D of src, vmult, D2H of dst every step
         n_local = src.numel()
-        hs = torch.empty(n_local, dtype=src.dtype).pin_memory()
-        hd = torch.empty(n_local, dtype=src.dtype).pin_memory()
-        hs.copy_(src.cpu())
+        esz = src.element_size()
         e_steps = max(3, min(args.steps, 10))
-        # two host buffer pairs / device staging slots / streams: the upload of step i+1 overlaps the
-        # download of step i (full-duplex PCIe); every step still moves its own src up and dst down
-        hs2 = torch.empty(n_local, dtype=src.dtype).pin_memory()
-        hd2 = torch.empty(n_local, dtype=src.dtype).pin_memory()
-        hs2.copy_(hs)
-        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-        bufs = [(hd, hs), (hd2, hs2)]
+        hbuf = [(torch.empty(n_local, dtype=src.dtype).pin_memory(), torch.empty(n_local, dtype=src.dtype).pin_memory()) for _ in range(2)]  # (dst, src)
+        hbuf[0][1].copy_(src.cpu())
+        hbuf[1][1].copy_(hbuf[0][1])
+        main = torch.cuda.current_stream()
+        if world == 1:
+            # C ABI entry point on host vectors; two staging slots on two streams: the upload of step i+1 overlaps
+            # the download of step i (full-duplex PCIe); every step still moves its own src up and dst down
+            streams = [torch.cuda.Stream(), torch.cuda.Stream()]
 
-        def host_step(i):
-            with torch.cuda.stream(streams[i % 2]):
-                d_, s_ = bufs[i % 2]
-                if world == 1:
-                    op.vmult_host(d_, s_, zero_dst=True, slot=i % 2)  # C ABI entry point on host vectors
-                else:
-                    src.copy_(s_, non_blocking=True)
-                    op.vmult(dst, src, zero_dst=True)  # ghost import / compress inside
-                    d_.copy_(dst, non_blocking=True)
+            def host_step(i):
+                with torch.cuda.stream(streams[i % 2]):
+                    op.vmult_host(hbuf[i % 2][0], hbuf[i % 2][1], zero_dst=True, slot=i % 2)
 
-        if world > 1:
-            streams = [torch.cuda.current_stream(), torch.cuda.current_stream()]  # one vector pair: no overlap across steps
+            def drain():
+                for s_ in streams:
+                    main.wait_stream(s_)
+
+            for s_ in streams:
+                s_.wait_stream(main)
+        else:
+            # partitioned: two device vector pairs; an upload stream and a download stream run beside the vmult
+            # stream, so that the copies of steps i+1 / i-1 overlap the vmult (ghost exchange inside) of step i
+            up, down = torch.cuda.Stream(), torch.cuda.Stream()
+            if args.exchange == "peer":
+                dev = [(dst, src), (dst, src)]  # the registered pair is the only one the peer path takes: no overlap across steps
+            else:
+                dev = [(dst, src), (op.initialize_dof_vector(), op.initialize_dof_vector())]
+            ev_up = [torch.cuda.Event() for _ in range(2)]
+            ev_mv = [torch.cuda.Event() for _ in range(2)]
+            ev_dn = [torch.cuda.Event() for _ in range(2)]
+            for e_ in ev_mv + ev_dn:
+                e_.record(main)
+
+            def host_step(i):
+                d_, s_ = dev[i % 2]
+                with torch.cuda.stream(up):
+                    up.wait_event(ev_mv[i % 2])  # the vmult that last read this src has finished
+                    s_.copy_(hbuf[i % 2][1], non_blocking=True)
+                    ev_up[i % 2].record(up)
+                main.wait_event(ev_up[i % 2])
+                main.wait_event(ev_dn[i % 2])  # the download that last read this dst has finished
+                op.vmult(d_, s_, zero_dst=True)  # ghost import / compress inside
+                ev_mv[i % 2].record(main)
+                with torch.cuda.stream(down):
+                    down.wait_event(ev_mv[i % 2])
+                    hbuf[i % 2][0].copy_(d_, non_blocking=True)
+                    ev_dn[i % 2].record(down)
+
+            def drain():
+                main.wait_stream(up)
+                main.wait_stream(down)
+
         for i in range(2):
             host_step(i)
+        drain()
         torch.cuda.synchronize()
         if barrier:
             barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for s_ in streams:
-            s_.wait_stream(torch.cuda.current_stream())
+        if world == 1:
+            for s_ in streams:
+                s_.wait_stream(main)
         for i in range(e_steps):
             host_step(i)
-        for s_ in streams:
-            torch.cuda.current_stream().wait_stream(s_)
+        drain()
         e1.record()
         torch.cuda.synchronize()
         if barrier:
@@ -427,28 +455,66 @@ def run():
             t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
-        esz = src.element_size()
         out["e2e"] = {"value": n_dofs_global / (e_ms / e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_local * esz),
                       "d2h_bytes_per_step": int(n_local * esz), "steps": e_steps,
                       "note": "mfhn_op_vmult_host_slot: pinned host src -> device, vmult into a zeroed device dst, dst -> pinned host, every step; "
                               "two staging slots on two streams so that the upload of step i+1 overlaps the download of step i; PCIe-bound"}
         if world > 1:
-            out["e2e"]["note"] = "per rank: pinned host src -> device, partitioned vmult with ghost exchange, dst -> pinned host; bytes are per rank"
+            out["e2e"]["note"] = ("per rank: pinned host src -> device, partitioned vmult with ghost exchange, dst -> pinned host, every step; two vector pairs, "
+                                  "upload / download streams beside the vmult stream; bytes are per rank")
+            del hbuf
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.minimal:
         cb, _, _ = run_cpu(args, mf, args.degree, 5)
         out["cpu_baseline"] = cb
 
-    if args.sweep and world == 1 and rank == 0:
+    if world == 1 and rank == 0 and not args.minimal and (args.sweep or not args.no_sweep):
         from bench_dist import degree_sweep
 
-        out["degree_sweep"] = degree_sweep(mfhn, torch, args, time_vmult)
+        del src, dst
+        torch.cuda.empty_cache()
+        src = dst = None
+        out["degree_sweep"] = degree_sweep(mfhn, torch, args, time_vmult, peaks()[0], full=args.sweep)
     if args.stages and world == 1 and rank == 0:
         from bench_dist import stage_benchmarks
 
-        del op, src, dst
+        del op
+        src = dst = None
         torch.cuda.empty_cache()
         out["stages"] = stage_benchmarks(mfhn, torch, args, L, time_vmult)
+
+    if world == 8 and not args.no_weak and not args.minimal and args.refinements is None:
+        # weak scaling (BASELINE.json config 4): the next finer mesh on 8 GPUs (annulus L=10, k=4: 1.124 B DoFs, 140.5 M per GPU).
+        # Not comparable with the N=1 line DoF for DoF: the finer mesh has half the share of cells with hanging nodes, so
+        # its efficiency is quoted against this run's own rank-local cell loops.
+        del op, prob, mf
+        src = dst = None
+        torch.cuda.empty_cache()
+        prob = build_problem(mfhn, args, L + 1, rank, world)
+        op, mf = prob["op"], prob["mf"]
+        if args.exchange == "peer":
+            dst, src = prob["comm"].enable_peer()
+        else:
+            src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        prob["fill_src"](src)
+        w_ms, _ = time_vmult(torch, op, dst, src, max(args.steps // 2, 5), 3, barrier)
+        t = torch.tensor([w_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w_ms = float(t.item()) / max(args.steps // 2, 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            op.vmult_range(dst, src, 0, mf.n_cells)
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        loc = [float(a[0]) for a in allr]
+        out["weak_scaling"] = {"workload": f"{args.geometry} L={L + 1}", "n_dofs": int(prob["n_dofs"]), "n_cells": int(prob["n_cells_global"]),
+                               "n_cells_hn": int(prob["n_cells_hn_global"]), "value": prob["n_dofs"] / (w_ms * 1e-3) / 1e9, "unit": UNIT,
+                               "ms_per_step": w_ms, "local_cell_loop_ms": [round(x, 4) for x in loc],
+                               "efficiency_vs_local_cell_loop": max(loc) / w_ms, "exchange": args.exchange}
 
     if world > 1:
         dist.destroy_process_group()

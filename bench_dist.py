@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import numpy as np
 
+KERNEL_NAMES = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch", 6: "bulk", 7: "runs"}
+
 
 def build_problem(mfhn, args, L, rank, world):
     import torch
@@ -35,40 +37,108 @@ def build_problem(mfhn, args, L, rank, world):
         i = torch.arange(src.numel(), device=src.device, dtype=torch.float64)
         src.copy_(torch.sin(1e-3 * i).to(src.dtype))
 
-    kname = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch", 6: "bulk"}[int(op.query("kernel"))]
+    kname = KERNEL_NAMES[int(op.query("kernel"))]
     return {"op": op, "mf": mf, "dh": dh, "tria": tria, "n_dofs": dh.n_dofs(), "n_cells_global": tria.n_active_cells(),
             "n_cells_hn_global": tria.n_cells_with_hanging_nodes(), "fill_src": fill_src, "kernel_name": kname,
             "partition": partition, "launches_per_step": launches, "comm": comm}
 
 
-def degree_sweep(mfhn, torch, args, time_vmult):
-    """degrees 1..8 on the annulus, double and float, with and
-    without constraints, all kernels."""
+def degree_sweep(mfhn, torch, args, time_vmult, hbm_peak, full=False):
+    """BASELINE.json metric "per degree 1-8" (configs 2 and 3): every degree on the annulus mesh in double and float,
+    with and without constraints, through the kernel AUTO picks; frac = accumulating-vmult bytes / time / HBM peak.
+    L = 9 for k <= 4 and 8 above; full=True adds L = 10 for k = 1, 2 (the L = 9 problems have 2.3 M / 18 M
+    DoFs only) and the other kernels."""
     res = []
     for k in range(1, 9):
-        L = 9 if k <= 4 else 8
-        tria = mfhn.Triangulation(args.geometry, L, "p4est")
-        dh = mfhn.DoFHandler(tria, k)
-        mf = mfhn.MatrixFree(dh)
-        for number in ("double", "float"):
-            row = {"degree": k, "L": L, "number": number, "n_dofs": dh.n_dofs(), "n_cells": mf.n_cells}
-            op = mfhn.LaplaceOperator(mf, number=number)
-            src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
-            src.fill_(1.0)
-            for kern in ("plane", "separable", "qpoint"):
-                try:
-                    op.set_kernel(kern)
-                except mfhn.MfhnError:
-                    continue
+        base = (9 if k <= 4 else 8) if args.refinements is None else max(args.refinements - (0 if k <= 4 else 1), 2)
+        for L in ([base, base + 1] if (full and k <= 2) else [base]):
+            tria = mfhn.Triangulation(args.geometry, L, "p4est")
+            dh = mfhn.DoFHandler(tria, k)
+            mf = mfhn.MatrixFree(dh)
+            for number in ("double", "float"):
+                op = mfhn.LaplaceOperator(mf, number=number)
+                row = {"degree": k, "L": L, "number": number, "n_dofs": dh.n_dofs(), "kernel": KERNEL_NAMES[int(op.query("kernel"))]}
+                src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+                i = torch.arange(src.numel(), device=src.device, dtype=torch.float64)
+                src.copy_(torch.sin(1e-3 * i).to(src.dtype))
+                t = {}
                 for ac in (True, False):
                     op.set_apply_constraints(ac)
-                    _, per = time_vmult(torch, op, dst, src, 10, 3)
-                    row[f"{kern}{'' if ac else '_noconstr'}_gdofs"] = dh.n_dofs() / (float(np.mean(per)) * 1e-3) / 1e9
-            row["algorithmic_bytes"] = op.query("algorithmic_bytes")
-            res.append(row)
-            del op, src, dst
-            torch.cuda.empty_cache()
+                    _, per = time_vmult(torch, op, dst, src, 8, 3)
+                    t[ac] = float(np.mean(per))
+                row["gdofs"] = round(dh.n_dofs() / (t[True] * 1e-3) / 1e9, 2)
+                row["gdofs_no_constraints"] = round(dh.n_dofs() / (t[False] * 1e-3) / 1e9, 2)
+                row["hn_overhead_percent"] = round(100.0 * (t[True] / t[False] - 1.0), 1)
+                row["frac_hbm"] = round(op.query("algorithmic_bytes_accumulate") / (t[True] * 1e-3) / 1e9 / hbm_peak, 3)
+                if full:
+                    op.set_apply_constraints(True)
+                    for kern in ("plane", "bulk", "runs", "separable", "qpoint"):
+                        try:
+                            op.set_kernel(kern)
+                            _, per = time_vmult(torch, op, dst, src, 5, 2)
+                            row[f"{kern}_gdofs"] = round(dh.n_dofs() / (float(np.mean(per)) * 1e-3) / 1e9, 2)
+                        except mfhn.MfhnError:
+                            continue
+                res.append(row)
+                del op, src, dst
+                torch.cuda.empty_cache()
     return res
+
+
+def parity_check(mfhn, torch, dist, args, rank, world, device):
+    """Partitioned vmult (both exchanges: NCCL import / compress and peer-memory access) against the one-GPU operator
+    of the same small mesh with the reference's non-constant test vector src = sum_d sin(x_d) (benchmark_03.h:362-378);
+    the one-GPU operator itself is pinned against the oracle in tests/.  A constant vector would not notice a broken
+    ghost -> owner compress.  Returns {exchange: max |y_partitioned - y_one_gpu| / max |y_one_gpu|}."""
+    from importlib import import_module
+
+    distributed = import_module("dealii-matrixfree-hanging-nodes_b200.distributed")
+    L = 6 if args.geometry == "annulus" else 5
+    if args.degree >= 6:
+        L -= 1
+    tria = mfhn.Triangulation(args.geometry, L, "p4est")
+    dtype = torch.float64 if args.number == "double" else torch.float32
+    # whole mesh on this GPU (serial numbering of the same mesh: compare through the support points)
+    dh1 = mfhn.DoFHandler(tria, args.degree)
+    op1 = mfhn.LaplaceOperator(mfhn.MatrixFree(dh1), number=args.number, kernel=args.kernel)
+    x1 = torch.from_numpy(np.sin(dh1.support_points()).sum(axis=1)).to(device=device, dtype=dtype)
+    s1, d1 = op1.initialize_dof_vector(), op1.initialize_dof_vector()
+    s1.copy_(x1)
+    op1.vmult(d1, s1)
+    ref_scale = float(d1.abs().max())
+    y1 = d1.double().cpu().numpy()
+    dhp = mfhn.DoFHandler(tria, args.degree, world, tria.partition(world, args.hn_weight))
+    # serial index of every DoF of the rank-major partitioned numbering, through the cell-wise (unsubstituted) index arrays
+    cells = np.arange(tria.n_active_cells())
+    r1 = dh1.fill(cells, raw=True, substituted=False, masks=False, h=False)[0]
+    rp = dhp.fill(cells, raw=True, substituted=False, masks=False, h=False)[0]
+    to_serial = np.zeros(dhp.n_dofs(), dtype=np.int64)
+    to_serial[rp.reshape(-1).astype(np.int64)] = r1.reshape(-1).astype(np.int64)
+    mf = mfhn.MatrixFree(dhp, rank)
+    mfhn.exchange_import_indices(mf.partitioner)
+    op = mfhn.LaplaceOperator(mf, number=args.number, kernel=args.kernel)
+    comm = distributed.GhostExchange(op)
+    op.attach_communicator(comm)
+    b, e = mf.partitioner.begin, mf.partitioner.end
+    xo = x1[torch.from_numpy(to_serial[b:e]).to(device)]
+    ref = torch.from_numpy(y1[to_serial[b:e]]).to(device)
+    out = {}
+    for exchange in ("nccl", "peer"):
+        if exchange == "peer":
+            dst, src = comm.enable_peer()
+        else:
+            src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        src.zero_()
+        src[:e - b] = xo
+        for _ in range(2):  # twice: the second application starts from a used ghost section
+            op.vmult(dst, src, zero_dst=True)
+        err = (dst[:e - b].double() - ref).abs().max().reshape(1) / ref_scale
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        out[exchange] = float(err.item())
+    out["mesh"] = f"{args.geometry} L={L}, {tria.n_active_cells()} cells, {dh1.n_dofs()} DoFs, src = sum sin(x_d)"
+    dist.barrier()
+    del comm, op
+    return out
 
 
 def stage_benchmarks(mfhn, torch, args, L, time_vmult):

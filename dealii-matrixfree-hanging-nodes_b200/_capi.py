@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfhn.so")
+LIB_PATH = os.environ.get("MFHN_LIB") or os.path.join(_HERE, "libmfhn.so")  # MFHN_LIB: development builds side by side
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -42,7 +42,13 @@ struct RunsCfg
   static constexpr int RW    = 4 + 64 * BR + 32 * NT;   // 32-bit words of a batch record
   static constexpr int idle  = 32 - P::lanes;           // idle lanes mirror lane - idle (same half-warp: broadcast loads)
   static constexpr int elems = P::cpw * (P::cs > cap ? P::cs : cap);
-  static constexpr int warps = 4;
+#ifndef MFHN_RUNS_SCATTER_HOIST
+#define MFHN_RUNS_SCATTER_HOIST 1
+#endif
+#ifndef MFHN_RUNS_WARPS
+#define MFHN_RUNS_WARPS 4
+#endif
+  static constexpr int warps = MFHN_RUNS_WARPS;
   static constexpr int smem_per_warp = round_up_to(elems * (int)sizeof(Number), 16) + 16; // + mbarrier
   static constexpr int smem  = warps * smem_per_warp;
   static_assert(n3 <= cap, "staging area too small");
@@ -215,11 +221,20 @@ __global__ void __launch_bounds__(RunsCfg<n, Number>::warps * 32, OCC) runs_cell
 
   // ---- scatter ---------------------------------------------------------------------------
   // the results go from registers straight to the staging layout (descriptors and positions are loaded again
-  // instead of living through the sweeps)
+  // instead of living through the sweeps); all index loads of the scatter are issued up front
 #pragma unroll
   for (int q = 0; q < R::NT; ++q) tab[q] = __ldg(tp + q * 32);
 #pragma unroll
   for (int r = 0; r < R::BR; ++r) bd[r] = __ldg(bp + r * 32);
+#if MFHN_RUNS_SCATTER_HOIST
+#pragma unroll
+  for (int u2 = 0; u2 < R::SU; ++u2)
+    {
+      g0[u2]  = u2 < p.sr ? __ldg(sp_i + u2 * 32) : bulk_invalid;
+      sp0[u2] = u2 < p.sr ? __ldg(sp_p + u2 * 32) : 0u;
+    }
+#endif
+  const unsigned z0 = lane < nz ? __ldg(p.zpos + hdr.y + lane) : 0xffffffffu;
   if (active && valid)
     {
       Number *S = A + c * R::cap;
@@ -227,14 +242,26 @@ __global__ void __launch_bounds__(RunsCfg<n, Number>::warps * 32, OCC) runs_cell
       for (int j = 0; j < n * n; ++j) S[(tab[j / 4] >> (8 * (j % 4))) & 0xffu] = u[j / n][j % n];
     }
   // entries of the copied ranges that do not belong to the cell add into foreign vector entries: they must hold zero
-  for (int i = lane; i < nz; i += 32) A[__ldg(p.zpos + hdr.y + i)] = Number(0);
+  if (z0 != 0xffffffffu) A[z0] = Number(0);
+  for (int i = lane + 32; i < nz; i += 32) A[__ldg(p.zpos + hdr.y + i)] = Number(0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // staging writes -> visible to the bulk engine
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < R::BR; ++r)
     if (bd[r].y >> 16) bulk_copy<false>(smem_u32(A + (bd[r].y & 0xffffu)), dst + bd[r].x, 0u, (bd[r].y >> 16) * 16u);
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  for (int r0 = 0; r0 < p.sr; r0 += R::SU)
+#if !MFHN_RUNS_SCATTER_HOIST
+#pragma unroll
+  for (int u2 = 0; u2 < R::SU; ++u2)
+    {
+      g0[u2]  = u2 < p.sr ? __ldg(sp_i + u2 * 32) : bulk_invalid;
+      sp0[u2] = u2 < p.sr ? __ldg(sp_p + u2 * 32) : 0u;
+    }
+#endif
+#pragma unroll
+  for (int u2 = 0; u2 < R::SU; ++u2)
+    if (g0[u2] != bulk_invalid) atomicAdd(dst + g0[u2], A[sp0[u2]]);
+  for (int r0 = R::SU; r0 < p.sr; r0 += R::SU)
     {
       uint32_t g[R::SU];
       unsigned sp[R::SU];

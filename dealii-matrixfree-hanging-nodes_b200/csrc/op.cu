@@ -418,6 +418,23 @@ struct Dist
     }                                                                                            \
   while (0)
 
+// ncclGroupStart ... ncclGroupEnd around f: an error inside still closes the group before it propagates
+template <typename F>
+void nccl_group(NcclApi &nccl, F &&f)
+{
+  NCCL_CHECK(nccl.GroupStart());
+  try
+    {
+      f();
+    }
+  catch (...)
+    {
+      nccl.GroupEnd();
+      throw;
+    }
+  NCCL_CHECK(nccl.GroupEnd());
+}
+
 void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero_dst)
 {
   Operator &op  = *d.op;
@@ -435,14 +452,14 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   CUDA_CHECK(cudaEventRecord(d.ev[0], main));
   CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[0], 0));
   // owners -> ghosts (update_ghost_values)
-  NCCL_CHECK(nccl.GroupStart());
-  for (size_t i = 0; i < d.ghost_peers.size(); ++i)
-    NCCL_CHECK(nccl.Recv(srcb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
-                         d.ghost_peers[i], d.comm, d.comm_stream));
-  for (size_t i = 0; i < d.import_peers.size(); ++i)
-    NCCL_CHECK(nccl.Send(static_cast<char *>(d.d_send) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
-                         d.import_peers[i], d.comm, d.comm_stream));
-  NCCL_CHECK(nccl.GroupEnd());
+  nccl_group(nccl, [&] {
+    for (size_t i = 0; i < d.ghost_peers.size(); ++i)
+      NCCL_CHECK(nccl.Recv(srcb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
+                           d.ghost_peers[i], d.comm, d.comm_stream));
+    for (size_t i = 0; i < d.import_peers.size(); ++i)
+      NCCL_CHECK(nccl.Send(static_cast<char *>(d.d_send) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
+                           d.import_peers[i], d.comm, d.comm_stream));
+  });
   CUDA_CHECK(cudaEventRecord(d.ev[1], d.comm_stream));
   if (d.seg[1] > d.seg[0]) op_vmult_range(op, dst, src, main, d.seg[0], d.seg[1]); // interior A overlaps the import
   CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[1], 0));
@@ -452,14 +469,14 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   CUDA_CHECK(cudaEventRecord(d.ev[2], main));
   CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[2], 0));
   // ghosts -> owners (compress, add)
-  NCCL_CHECK(nccl.GroupStart());
-  for (size_t i = 0; i < d.import_peers.size(); ++i)
-    NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
-                         d.import_peers[i], d.comm, d.comm_stream));
-  for (size_t i = 0; i < d.ghost_peers.size(); ++i)
-    NCCL_CHECK(nccl.Send(dstb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
-                         d.ghost_peers[i], d.comm, d.comm_stream));
-  NCCL_CHECK(nccl.GroupEnd());
+  nccl_group(nccl, [&] {
+    for (size_t i = 0; i < d.import_peers.size(); ++i)
+      NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
+                           d.import_peers[i], d.comm, d.comm_stream));
+    for (size_t i = 0; i < d.ghost_peers.size(); ++i)
+      NCCL_CHECK(nccl.Send(dstb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
+                           d.ghost_peers[i], d.comm, d.comm_stream));
+  });
   CUDA_CHECK(cudaEventRecord(d.ev[3], d.comm_stream));
   if (d.seg[2] > d.seg[1]) op_vmult_range(op, dst, src, main, d.seg[1], d.seg[2]); // interior B overlaps the compress
   CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
@@ -787,6 +804,15 @@ int mfhn_dist_create(mfhn_op h, const mfhn_dist_desc *dd, mfhn_dist *out)
     d->ghost_peers.assign(dd->ghost_peers, dd->ghost_peers + dd->n_ghost_peers);
     d->ghost_begin.assign(dd->ghost_begin, dd->ghost_begin + dd->n_ghost_peers);
     d->ghost_end.assign(dd->ghost_end, dd->ghost_end + dd->n_ghost_peers);
+    if (dd->world < 1 || dd->rank < 0 || dd->rank >= dd->world) throw InvalidArgument("rank / world out of range");
+    if (d->import_off[0] != 0) throw InvalidArgument("import offsets must start at 0");
+    for (size_t i = 0; i < d->import_peers.size(); ++i)
+      {
+        if (d->import_peers[i] < 0 || d->import_peers[i] >= dd->world || d->import_peers[i] == dd->rank) throw InvalidArgument("import peer out of range");
+        if (d->import_off[i + 1] < d->import_off[i]) throw InvalidArgument("import offsets must be ascending");
+      }
+    for (const int pr : d->ghost_peers)
+      if (pr < 0 || pr >= dd->world || pr == dd->rank) throw InvalidArgument("ghost peer out of range");
     d->n_import = d->import_off.back();
     for (long long i = 0; i < d->n_import; ++i)
       if (dd->import_indices[i] < 0 || dd->import_indices[i] >= op.n_owned) throw InvalidArgument("import index out of range");
@@ -865,13 +891,13 @@ int mfhn_op_inverse_diagonal(mfhn_op h, mfhn_dist dh, void *inv_diag, void *stre
         Dist &d       = *reinterpret_cast<Dist *>(dh);
         NcclApi &nccl = NcclApi::get();
         char *db      = static_cast<char *>(inv_diag);
-        NCCL_CHECK(nccl.GroupStart());
-        for (size_t i = 0; i < d.import_peers.size(); ++i)
-          NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
-                               d.import_peers[i], d.comm, st));
-        for (size_t i = 0; i < d.ghost_peers.size(); ++i)
-          NCCL_CHECK(nccl.Send(db + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0, d.ghost_peers[i], d.comm, st));
-        NCCL_CHECK(nccl.GroupEnd());
+        nccl_group(nccl, [&] {
+          for (size_t i = 0; i < d.import_peers.size(); ++i)
+            NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
+                                 d.import_peers[i], d.comm, st));
+          for (size_t i = 0; i < d.ghost_peers.size(); ++i)
+            NCCL_CHECK(nccl.Send(db + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0, d.ghost_peers[i], d.comm, st));
+        });
         run_unpack_add(op.number, inv_diag, d.d_recv, d.d_import_idx, d.n_import, true, st);
         if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(db + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, st));
       }
