@@ -187,6 +187,12 @@ def problem_config(args, workload, tria, n_dofs, world):
             "exchange": args.exchange if world > 1 else None}
 
 
+def log(msg):
+    """Progress on stderr (MFHN_BENCH_VERBOSE=1): where a multi-rank run is when it has to be killed."""
+    if os.environ.get("MFHN_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     # keep stdout clean for the ONE JSON line: library chatter (e.g. "NCCL version ...") goes to stderr
     real_stdout = os.dup(1)
@@ -198,6 +204,12 @@ def main():
         os.dup2(real_stdout, 1)
     if line is not None:
         print(line, flush=True)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # partitioned runs: leave without tearing down NCCL communicators and IPC mappings rank by rank (the ranks would
+        # wait for each other's teardown in interpreter-exit order); the process group was destroyed in run()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run():
@@ -240,8 +252,10 @@ def run():
     t_setup = time.perf_counter()
     from bench_dist import build_problem  # noqa: E402  (shared by the 1-GPU and the partitioned path)
 
+    log("setup")
     prob = build_problem(mfhn, args, L, rank, world)
     op, mf, n_dofs_global = prob["op"], prob["mf"], prob["n_dofs"]
+    log("problem built")
     if world > 1 and args.exchange == "peer":
         dst, src = prob["comm"].enable_peer()  # exportable vector pair, peers' vectors mapped through CUDA IPC
     else:
@@ -253,8 +267,10 @@ def run():
     if world > 1 and args.graph:
         graph = prob["comm"].capture(op, dst, src)
         dst.zero_()
+    log("timed loop")
     with ClockSampler(local_rank) as clocks:
         total_ms, per = time_vmult(torch, op, dst, src, args.steps, args.warmup, barrier, graph)
+    log("timed loop done")
     rank_info = None
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -283,7 +299,9 @@ def run():
         # partitioned vmult against the one-GPU operator on a small mesh, non-constant vector, both exchanges
         from bench_dist import parity_check
 
-        parity = parity_check(mfhn, torch, dist, args, rank, world, src.device)
+        log("parity check")
+        parity, parity_keep = parity_check(mfhn, torch, dist, args, rank, world, src.device)
+        log("parity check done")
         tol = 1e-12 if args.number == "double" else 1e-5
         assert parity["nccl"] < tol and parity["peer"] < tol, f"partitioned vmult differs from the one-GPU operator: {parity}"
 
@@ -375,6 +393,7 @@ def run():
                                 "index_gdofs": n_dofs_global / (float(np.mean(p1)) * 1e-3) / 1e9}
         del op_plain, mf_plain
 
+    log("roofline done")
     if not args.no_e2e and not args.minimal:
         # end to end with HOST vectors: H2D of src, vmult, D2H of dst every step
         n_local = src.numel()
@@ -432,10 +451,12 @@ def run():
                 main.wait_stream(up)
                 main.wait_stream(down)
 
+        log("e2e warm-up")
         for i in range(2):
             host_step(i)
         drain()
         torch.cuda.synchronize()
+        log("e2e timed")
         if barrier:
             barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -487,9 +508,8 @@ def run():
         # weak scaling (BASELINE.json config 4): the next finer mesh on 8 GPUs (annulus L=10, k=4: 1.124 B DoFs, 140.5 M per GPU).
         # Not comparable with the N=1 line DoF for DoF: the finer mesh has half the share of cells with hanging nodes, so
         # its efficiency is quoted against this run's own rank-local cell loops.
-        del op, prob, mf
-        src = dst = None
-        torch.cuda.empty_cache()
+        strong_keep = (op, prob, mf, src, dst)  # no communicator teardown in the middle of the run (see parity_check)
+        log("weak-scaling problem")
         prob = build_problem(mfhn, args, L + 1, rank, world)
         op, mf = prob["op"], prob["mf"]
         if args.exchange == "peer":
@@ -517,6 +537,8 @@ def run():
                                "efficiency_vs_local_cell_loop": max(loc) / w_ms, "exchange": args.exchange}
 
     if world > 1:
+        log("leaving")
+        dist.barrier()
         dist.destroy_process_group()
     return json.dumps(out) if rank == 0 else None
 

@@ -4,6 +4,13 @@ from __future__ import annotations
 
 import numpy as np
 
+def _log(msg):
+    import os, sys, time
+
+    if os.environ.get("MFHN_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 KERNEL_NAMES = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch", 6: "bulk", 7: "runs"}
 
 
@@ -117,6 +124,7 @@ def parity_check(mfhn, torch, dist, args, rank, world, device):
     mf = mfhn.MatrixFree(dhp, rank)
     mfhn.exchange_import_indices(mf.partitioner)
     op = mfhn.LaplaceOperator(mf, number=args.number, kernel=args.kernel)
+    _log("parity: communicator")
     comm = distributed.GhostExchange(op)
     op.attach_communicator(comm)
     b, e = mf.partitioner.begin, mf.partitioner.end
@@ -124,21 +132,27 @@ def parity_check(mfhn, torch, dist, args, rank, world, device):
     ref = torch.from_numpy(y1[to_serial[b:e]]).to(device)
     out = {}
     for exchange in ("nccl", "peer"):
+        _log(f"parity: {exchange}")
         if exchange == "peer":
             dst, src = comm.enable_peer()
         else:
             src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+        _log("parity: vectors")
         src.zero_()
         src[:e - b] = xo
         for _ in range(2):  # twice: the second application starts from a used ghost section
             op.vmult(dst, src, zero_dst=True)
+        torch.cuda.synchronize()
+        _log("parity: applied")
         err = (dst[:e - b].double() - ref).abs().max().reshape(1) / ref_scale
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         out[exchange] = float(err.item())
     out["mesh"] = f"{args.geometry} L={L}, {tria.n_active_cells()} cells, {dh1.n_dofs()} DoFs, src = sum sin(x_d)"
     dist.barrier()
-    del comm, op
-    return out
+    _log("parity: done")
+    # the communicator (a second NCCL communicator and IPC mappings) stays alive until the process ends: tearing it down
+    # in the middle of the run blocked one rank on this pool
+    return out, (comm, op, mf, dhp, tria)
 
 
 def stage_benchmarks(mfhn, torch, args, L, time_vmult):

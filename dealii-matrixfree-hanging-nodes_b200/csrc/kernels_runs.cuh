@@ -25,6 +25,10 @@
 #include <cstring>
 
 
+#ifndef MFHN_RUNS_CAP_PCT
+#define MFHN_RUNS_CAP_PCT 50 // staging room beyond the (k+1)^3 cell entries: copied foreign entries, alignment, placement slack
+#endif
+
 namespace mfhn
 {
 template <int n, typename Number>
@@ -33,7 +37,7 @@ struct RunsCfg
   using P                    = PlaneCfg<n, Number>;
   static constexpr int E     = 16 / (int)sizeof(Number); // entries per 16 bytes
   static constexpr int n3    = n * n * n;
-  static constexpr int cap0  = round_up_to(n3 + n3 / 2, 8);
+  static constexpr int cap0  = round_up_to(n3 + n3 * MFHN_RUNS_CAP_PCT / 100, 8);
   static constexpr int cap   = cap0 > 256 ? 256 : cap0; // staging entries per cell (positions are bytes)
   static constexpr int NT    = (n * n + 3) / 4;         // position words per thread
   static constexpr int BR    = 2;                       // descriptor rounds: at most 64 bulk copies per warp batch

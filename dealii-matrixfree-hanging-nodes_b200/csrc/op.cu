@@ -164,6 +164,17 @@ void launch_diagonal(Operator &op, const CellLoopParams &p, cudaStream_t stream)
   ++op.launches;
 }
 
+// The run-wise layout is built on first use (its placement pass takes seconds on 10^6 cells): from the operator's
+// device copy of the index array.
+void ensure_runs(Operator &op)
+{
+  if (op.runs.usable) return;
+  const int n = op.degree + 1;
+  std::vector<uint32_t> idx((size_t)op.n_cells * n * n * n);
+  if (!idx.empty()) CUDA_CHECK(cudaMemcpy(idx.data(), op.d_idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  runs_build(op.runs, n, op.number, op.n_cells, op.n_owned + op.n_ghost + op.vector_padding, idx.data());
+}
+
 void launch_kernel(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
 {
   if (kernel == MFHN_KERNEL_BASELINE)
@@ -206,6 +217,7 @@ void launch_kernel(Operator &op, int kernel, const CellLoopParams &p, cudaStream
     }
   else if (kernel == MFHN_KERNEL_RUNS)
     {
+      ensure_runs(op);
       // whole warp batches; the (at most cpw - 1) cells in front of an unaligned range go to the plane kernel
       const long long cpw = 32 / (op.degree + 1);
       const long long b0  = std::min((p.cell_begin + cpw - 1) / cpw * cpw, p.cell_end);
@@ -239,16 +251,19 @@ int resolve_kernel(const Operator &op)
   if (kernel == MFHN_KERNEL_AUTO)
     {
       kernel = op.geometry_type == MFHN_GEOM_CARTESIAN ? MFHN_KERNEL_PLANE : MFHN_KERNEL_QPOINT;
-      // measured on B200 (profiles/): the bulk-copy kernel wins for double at k = 4, 5 (the plane kernel is bound by
-      // the L1 data stage there); for float and k = 3 the plane kernel's gathers are cheap enough
-      if (kernel == MFHN_KERNEL_PLANE && op.number == MFHN_F64 && (op.degree == 4 || op.degree == 5) && op.bulk.usable) kernel = MFHN_KERNEL_BULK;
+      // measured on B200 (profiles/r2_kernel_choice.jsonl, annulus L=9 / L=8, GDoF/s double | float):
+      //   k=3: plane 82.6 | 99.8, runs 66.7 | 103.0;  k=4: plane 83.6 | 125.1, bulk 109.0 | 128.8, runs 122.2 | 132.8;
+      //   k=5: plane 93.6 | 139.2, bulk 120.1 | 141.1, runs 113.2 | 124.6;  k=1,2: plane ahead of runs by 20-50 %
+      if (kernel == MFHN_KERNEL_PLANE && op.degree == 4) kernel = MFHN_KERNEL_RUNS;
+      if (kernel == MFHN_KERNEL_PLANE && op.degree == 3 && op.number == MFHN_F32) kernel = MFHN_KERNEL_RUNS;
+      if (kernel == MFHN_KERNEL_PLANE && op.degree == 5 && op.bulk.usable) kernel = MFHN_KERNEL_BULK;
     }
   if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT)
     throw InvalidArgument("affine / general geometry requires MFHN_KERNEL_QPOINT");
   if (kernel == MFHN_KERNEL_BULK && !bulk_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
   if (kernel == MFHN_KERNEL_BULK && op.geometry_type == MFHN_GEOM_CARTESIAN && !op.bulk.usable)
     throw InvalidArgument("MFHN_KERNEL_BULK: the DoF numbering does not show contiguous cell-interior / face blocks");
-  if (kernel == MFHN_KERNEL_RUNS && (!runs_supported(op.degree + 1) || !op.runs.usable)) throw NotImplemented("MFHN_KERNEL_RUNS is available for degrees 1..5");
+  if (kernel == MFHN_KERNEL_RUNS && !runs_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_RUNS is available for degrees 1..5");
   if (kernel == MFHN_KERNEL_PATCH)
     throw NotImplemented("MFHN_KERNEL_PATCH (sorted-unique patch gather, round 1) was measured slower than the plane kernel and has been removed");
   if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_RUNS || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
@@ -365,7 +380,7 @@ Operator *op_create(const mfhn_op_desc &d)
       if (d.vector_padding < 0) throw InvalidArgument("negative vector padding");
       op->vector_padding = d.vector_padding;
       if (bulk_supported(n)) bulk_build(op->bulk, n, d.number, d.n_cells, nvec + d.vector_padding, d.dof_indices);
-      if (runs_supported(n)) runs_build(op->runs, n, d.number, d.n_cells, nvec + d.vector_padding, d.dof_indices);
+      // (the run-wise layout is built when MFHN_KERNEL_RUNS is first used: ensure_runs)
     }
   resolve_kernel(*op);
   return op.release();
@@ -694,7 +709,7 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
 {
   return guard([&] {
     if (!h || !what || !value) throw InvalidArgument("null argument");
-    const Operator &op = *reinterpret_cast<Operator *>(h);
+    Operator &op = *reinterpret_cast<Operator *>(h);
     const double n = op.degree + 1, n3 = n * n * n, s = op.number == MFHN_F64 ? 8 : 4;
     const double nvec = (double)(op.n_owned + op.n_ghost);
     const std::string w(what);
@@ -710,14 +725,18 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
       *value = (double)op.n_cells * (12 * n * n * (n * n + 2 * n) + 3 * n3);
     else if (w == "kernel")
       *value = (double)resolve_kernel(op);
+    else if (w.rfind("runs_", 0) == 0 && !runs_supported(op.degree + 1))
+      *value = -1.0;
     else if (w == "runs_bulk_copies") // bulk copies / single entries / zeroed entries of the run-wise layout, whole mesh
-      *value = op.runs.usable ? (double)op.runs.n_blocks : -1.0;
-    else if (w == "runs_single_entries")
-      *value = op.runs.usable ? (double)op.runs.n_singles : -1.0;
-    else if (w == "runs_zero_entries")
-      *value = op.runs.usable ? (double)op.runs.n_zero : -1.0;
-    else if (w == "runs_single_rounds") // rounds of the fixed-stride single-entry rows
-      *value = op.runs.usable ? (double)op.runs.sr : -1.0;
+      {
+        ensure_runs(op);
+        *value = (double)op.runs.n_blocks;
+      }
+    else if (w == "runs_single_entries" || w == "runs_zero_entries" || w == "runs_single_rounds")
+      {
+        ensure_runs(op);
+        *value = w == "runs_single_entries" ? (double)op.runs.n_singles : w == "runs_zero_entries" ? (double)op.runs.n_zero : (double)op.runs.sr; // sr: rounds of the fixed-stride single-entry rows
+      }
     else if (w == "runs_staging_wavefronts") // bank model of the staging reads (MFHN_RUNS_STATS=1 at creation), 2 per plane slot and batch = no conflict
       *value = (double)op.runs.staging_wavefronts;
     else if (w == "bulk_irregular_cells") // cells the bulk-copy kernel leaves to the plane kernel (-1: layout not usable)
@@ -1023,8 +1042,12 @@ int mfhn_vec_alloc(int64_t bytes, void **ptr)
 {
   return guard([&] {
     if (!ptr || bytes < 0) throw InvalidArgument("bad argument");
-    CUDA_CHECK(cudaMalloc(ptr, std::max<size_t>((size_t)bytes, 8)));
-    CUDA_CHECK(cudaMemset(*ptr, 0, std::max<size_t>((size_t)bytes, 8)));
+    // These vectors are exported with cudaIpcGetMemHandle.  cudaMalloc carves small requests out of shared 2 MiB
+    // blocks and the handle maps the BLOCK: a peer that opens it gets the block's base, not this pointer.  Whole
+    // 2 MiB multiples give every vector blocks of its own, so the opened pointer is the vector.
+    const size_t granule = (size_t)2 << 20, size = (std::max<size_t>((size_t)bytes, 8) + granule - 1) / granule * granule;
+    CUDA_CHECK(cudaMalloc(ptr, size));
+    CUDA_CHECK(cudaMemset(*ptr, 0, size));
   });
 }
 int mfhn_vec_free(void *ptr)

@@ -85,23 +85,27 @@ def test_vmult_without_constraints(mfhn, kernel):
 @pytest.mark.parametrize("number", ["double", "float"])
 @pytest.mark.parametrize("k", [3, 4, 5])
 def test_bulk_kernel_ranges_irregular_cells_and_alignment(mfhn, k, number):
-    """MFHN_KERNEL_BULK: cell ranges (the partitions of the overlap schedule), the cells left to the
-    plane kernel (a block that ends at the last vector entry) and the 16-byte alignment rule."""
+    """MFHN_KERNEL_BULK / MFHN_KERNEL_RUNS: cell ranges (the partitions of the overlap schedule, not aligned to warp
+    batches) and the 16-byte alignment rule."""
     import torch
 
     dh, mf, lay = _case(mfhn, "quadrant", 3, "p4est", k)
     x = _src(lay, "random")
     ref = operators.vmult_fast(lay, x)
     op = mfhn.LaplaceOperator(mf, number=number, kernel="bulk")
-    assert op.query("bulk_irregular_cells") >= 1  # the hex block of the last cell ends the vector
+    assert op.query("bulk_irregular_cells") == 0  # the padding behind the vectors takes the widened last block
     src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
     src.copy_(torch.from_numpy(x).to(src.dtype))
     cuts = [0, 7, 8, 50, mf.n_cells]
-    for b, e in zip(cuts[:-1], cuts[1:]):
-        op.vmult_range(dst, src, b, e)
-    torch.cuda.synchronize()
-    y = dst.cpu().numpy().astype(np.float64)
-    assert np.abs(y - ref).max() / np.abs(ref).max() < TOL[number]
+    for kern in ("bulk", "runs"):
+        op.set_kernel(kern)
+        dst.zero_()
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            op.vmult_range(dst, src, b, e)
+        torch.cuda.synchronize()
+        y = dst.cpu().numpy().astype(np.float64)
+        assert np.abs(y - ref).max() / np.abs(ref).max() < TOL[number], kern
+    assert op.query("runs_bulk_copies") >= mf.n_cells - 8 and op.query("runs_single_entries") > 0
     # unaligned views are rejected (bulk copies need 16-byte aligned addresses)
     big = torch.zeros(src.numel() + 8, dtype=src.dtype, device=src.device)
     with pytest.raises(mfhn.MfhnError):
