@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--geometry", default="annulus")
     ap.add_argument("--refinements", type=int, default=None)
-    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--degree", type=int, default=None)
     ap.add_argument("--number", default="double", choices=["double", "float"])
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
@@ -53,11 +53,17 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the compact degree sweep (degrees 1..8, double + float) of the default line")
     ap.add_argument("--no-weak", action="store_true", help="8 GPUs: skip the extra weak-scaling run on the next finer mesh")
     ap.add_argument("--stages", action="store_true", help="the reference's DG (SC) / CG (SC) decomposition and eta (benchmark_01.cc:189-220)")
+    ap.add_argument("--cg", action="store_true", help="BASELINE.json config 5: CG + point-Jacobi solve (degree 6 unless --degree is given), time per iteration split")
+    ap.add_argument("--cg-iterations", type=int, default=100)
+    ap.add_argument("--cg-tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="timed loop only (for profiler runs)")
     ap.add_argument("--graph", action="store_true", help="partitioned runs: replay a CUDA graph of one vmult (experimental: the capture of the NCCL p2p groups hung on this pool, so it is off by default)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.degree is None:
+        args.degree = 6 if args.cg else 4
+    return args
 
 
 def peaks():
@@ -249,8 +255,17 @@ def run():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         barrier = dist.barrier
 
-    t_setup = time.perf_counter()
     from bench_dist import build_problem  # noqa: E402  (shared by the 1-GPU and the partitioned path)
+
+    if args.cg:
+        from bench_dist import cg_benchmark
+
+        res = cg_benchmark(mfhn, torch, dist if world > 1 else None, args, L, rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return json.dumps(res) if rank == 0 else None
+    t_setup = time.perf_counter()
 
     log("setup")
     prob = build_problem(mfhn, args, L, rank, world)
@@ -388,9 +403,17 @@ def run():
         _, p1 = time_vmult(torch, op_plain, dst, src, 10, 3)
         op_plain.set_apply_constraints(False)
         _, p0 = time_vmult(torch, op_plain, dst, src, 10, 3)
+        # "mask" analogue: every warp takes the interpolation passes, constrained lines picked by per-lane predicates
+        op.set_hn_strategy("mask")
+        _, pm = time_vmult(torch, op, dst, src, 10, 3)
+        op.set_hn_strategy("branch")
         out["hn_strategies"] = {"sorted_overhead_percent": out["hn_overhead_percent"], "sorted_gdofs": value,
                                 "index_overhead_percent": 100.0 * (float(np.mean(p1)) / float(np.mean(p0)) - 1.0),
-                                "index_gdofs": n_dofs_global / (float(np.mean(p1)) * 1e-3) / 1e9}
+                                "index_gdofs": n_dofs_global / (float(np.mean(p1)) * 1e-3) / 1e9,
+                                "mask_overhead_percent": 100.0 * (float(np.mean(pm)) / float(np.mean(per_nc)) - 1.0),
+                                "mask_gdofs": n_dofs_global / (float(np.mean(pm)) * 1e-3) / 1e9,
+                                "note": "analogues of the reference's vectorisation types (benchmark_01.cc:70-116): index = plain Morton cell order, "
+                                        "sorted = cells grouped by constraint kind inside Morton windows (default), mask = branch-free, all warps interpolate"}
         del op_plain, mf_plain
 
     log("roofline done")

@@ -192,7 +192,25 @@ def stage_benchmarks(mfhn, torch, args, L, time_vmult):
     e1.record()
     torch.cuda.synchronize()
     res["hn_kernel_alone_ms"] = e0.elapsed_time(e1) / 10
-    del op, src, dst, vals
+    # DG (C): cell-local vectors, no quadrature-point work (benchmark_01.cc:189-199): t0 plain copy, t1 with interpolation
+    dvals = torch.zeros_like(vals)
+
+    def time_dg(ac):
+        op.set_apply_constraints(ac)
+        for _ in range(3):
+            op.dg_copy(dvals, vals)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            op.dg_copy(dvals, vals)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 10
+
+    t0, t1 = time_dg(False), time_dg(True)
+    op.set_apply_constraints(True)
+    res.update(t0_ms=t0, t1_ms=t1, eta1=eta(t0, t1))
+    del op, src, dst, vals, dvals
     torch.cuda.empty_cache()
     # DG (SC): private DoFs per cell
     class _DG:
@@ -212,3 +230,39 @@ def stage_benchmarks(mfhn, torch, args, L, time_vmult):
     _, t3 = time_vmult(torch, op, dst, src, 10, 3)
     res.update(t2_ms=float(t2.mean()), t3_ms=float(t3.mean()), eta3=eta(float(t2.mean()), float(t3.mean())))
     return res
+
+
+def cg_benchmark(mfhn, torch, dist, args, L, rank, world):
+    """BASELINE.json config 5: conjugate gradients with point-Jacobi on the adaptive mesh (degree 6 by default), the whole
+    iteration inside the library (mfhn_cg_solve: one vmult, two fused vector kernels, one batched 3-scalar all-reduce per
+    iteration).  The right-hand side is A x* for a random x*, so the system is consistent.  Reports the device time per
+    iteration split into vmult / vector kernels / all-reduce."""
+    prob = build_problem(mfhn, args, L, rank, world)
+    op, mf = prob["op"], prob["mf"]
+    n = op.n_owned
+    xs, b, x = op.initialize_dof_vector(), op.initialize_dof_vector(), op.initialize_dof_vector()
+    g = torch.Generator(device=xs.device)
+    g.manual_seed(1234 + rank)
+    xs[:n] = torch.rand(n, generator=g, device=xs.device, dtype=torch.float64).to(xs.dtype) - 0.5
+    op.vmult(b, xs, zero_dst=True)
+    inv = mfhn.inverse_diagonal(op)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    its, hist, split = mfhn.solve_cg(op, x, b, inverse=inv, rel_tol=args.cg_tol, max_iter=args.cg_iterations, check_every=10, timings=True)
+    t = torch.tensor([split["ms_total"], split["ms_vmult"], split["ms_vector_ops"], split["ms_allreduce"]], device=x.device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot, mv, vec, ar = (float(v) / max(its, 1) for v in t.tolist())
+    s = 8 if args.number == "double" else 4
+    n_dofs = prob["n_dofs"]
+    return {"metric": "cg_jacobi_time_per_iteration", "value": tot, "unit": "ms", "higher_is_better": False, "n_gpus": world,
+            "iterations": its, "residual_reduction": hist[-1] / hist[0] if hist and hist[0] > 0 else None,
+            "ms_per_iteration": {"total": tot, "vmult": mv, "vector_kernels": vec, "all_reduce": ar},
+            "gdofs_per_iteration": n_dofs / (tot * 1e-3) / 1e9,
+            "vector_kernels_bytes_per_iteration": 15 * s * n_dofs,  # update: 6 reads + 5 writes, dots: 3 reads (+ inverse diagonal)
+            "vector_kernels_gbs": 15 * s * n_dofs / (vec * 1e-3) / 1e9 if vec > 0 else None,
+            "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic (b = A x*, x* random)",
+            "config": {"workload": f"{args.geometry} L={L}, FE_Q({args.degree}), {args.number}, CG + point-Jacobi", "n_dofs": int(n_dofs),
+                       "n_cells": int(prob["n_cells_global"]), "kernel": prob["kernel_name"], "partition": prob["partition"],
+                       "tolerance": args.cg_tol, "max_iterations": args.cg_iterations}}

@@ -121,6 +121,8 @@ SIGNATURES = {
     "mfhn_op_set_apply_constraints": (c_int, [c_void_p, c_int]),
     "mfhn_op_set_kernel": (c_int, [c_void_p, c_int]),
     "mfhn_op_apply_hn": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "mfhn_op_dg_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mfhn_op_set_hn_strategy": (c_int, [c_void_p, c_int]),
     "mfhn_op_query": (c_int, [c_void_p, c_char_p, P(c_double)]),
     "mfhn_op_launch_count": (c_int64, [c_void_p]),
     "mfhn_pack": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

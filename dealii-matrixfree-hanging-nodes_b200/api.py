@@ -351,6 +351,19 @@ class LaplaceOperator:
     def set_apply_constraints(self, flag: bool):
         check(lib.mfhn_op_set_apply_constraints(self._h, int(flag)))
 
+    def set_hn_strategy(self, strategy: str):
+        """"branch" (default: a warp interpolates only if one of its cells is constrained) or "mask" (every warp takes the
+        passes, per-lane predicates) -- the reference's vectorisation types, benchmark_01.cc:70-116."""
+        check(lib.mfhn_op_set_hn_strategy(self._h, {"branch": 0, "mask": 1}[strategy]))
+
+    def dg_copy(self, dst_cells, src_cells):
+        """"DG (C)" stage (benchmark_01.cc:189-199): dst_cells += [W^T W] src_cells on cell-local [n_cells, (k+1)^3] arrays."""
+        torch = _torch()
+        n = self.mf.n_cells * (self.mf.degree + 1) ** 3
+        for v in (dst_cells, src_cells):
+            assert v.is_cuda and v.dtype == self.dtype and v.is_contiguous() and v.numel() == n
+        check(lib.mfhn_op_dg_copy(self._h, dst_cells.data_ptr(), src_cells.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+
     def set_kernel(self, kernel: str):
         check(lib.mfhn_op_set_kernel(self._h, capi.KERNELS[kernel]))
 

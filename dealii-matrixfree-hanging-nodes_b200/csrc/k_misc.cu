@@ -77,20 +77,14 @@ void launch_baseline_number(int degree, BaselineArrays &a, const uint32_t *d_idx
     }
 }
 
+// the three directional passes of the interpolation (or its transpose) on the n^3 values of one cell in shared memory;
+// thread l = a + n b handles one line per direction
 template <int n, typename Number>
-__global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n_cells, int transpose)
+__device__ __forceinline__ void hn_passes_block(Number *s, const int l, const unsigned mask, const bool transpose)
 {
-  // FEEvaluationHangingNodesFactory::apply on cell-local values (benchmark_00_likwid.cc:56-59)
-  __shared__ Number s[n * n * n];
-  const long long cell = blockIdx.x;
-  if (masks[cell] == 0) return; // unconstrained cell: nothing to interpolate (block-uniform)
-  const int l = threadIdx.x, a = l % n, b = l / n;
-  Number *g = values + cell * (n * n * n);
-  for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
+  const int a = l % n, b = l / n;
   unsigned face, edge, cb;
-  const unsigned mask = masks[cell];
   decode_mask(mask, face, edge, cb);
-  __syncthreads();
   for (int d = 0; d < 3; ++d)
     {
       Number *line   = s + (d == 0 ? n * (a + n * b) : d == 1 ? a + n * n * b : a + n * b);
@@ -104,7 +98,46 @@ __global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n
         }
       __syncthreads();
     }
+}
+
+template <int n, typename Number>
+__global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n_cells, int transpose)
+{
+  // FEEvaluationHangingNodesFactory::apply on cell-local values (benchmark_00_likwid.cc:56-59)
+  __shared__ Number s[n * n * n];
+  const long long cell = blockIdx.x;
+  if (masks[cell] == 0) return; // unconstrained cell: nothing to interpolate (block-uniform)
+  const int l = threadIdx.x;
+  Number *g = values + cell * (n * n * n);
+  for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
+  const unsigned mask = masks[cell];
+  __syncthreads();
+  hn_passes_block<n>(s, l, mask, transpose != 0);
   for (int z = 0; z < n; ++z) g[l + n * n * z] = s[l + n * n * z];
+}
+
+// "DG (C)" of the reference's stage decomposition (benchmark_01.cc:189-199, benchmark_01.h:617-677 with VectorType1):
+// every cell owns private DoFs, no quadrature-point work -- gather_plain [+ interpolation], [interpolation^T +]
+// scatter_plain, dst += values.  Cells without constraints skip shared memory altogether.
+template <int n, typename Number>
+__global__ void dg_copy_kernel(Number *dst, const Number *src, const uint8_t *masks, long long n_cells, int apply_constraints)
+{
+  __shared__ Number s[n * n * n];
+  const long long cell = blockIdx.x;
+  const int l          = threadIdx.x;
+  const unsigned mask  = apply_constraints ? masks[cell] : 0u;
+  const Number *g      = src + cell * (n * n * n);
+  Number *o            = dst + cell * (n * n * n);
+  if (mask == 0u)
+    {
+      for (int z = 0; z < n; ++z) o[l + n * n * z] += g[l + n * n * z];
+      return;
+    }
+  for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
+  __syncthreads();
+  hn_passes_block<n>(s, l, mask, false);
+  hn_passes_block<n>(s, l, mask, true);
+  for (int z = 0; z < n; ++z) o[l + n * n * z] += s[l + n * n * z];
 }
 
 template <typename Number>
@@ -123,6 +156,24 @@ void hn_only(int degree, void *values, const uint8_t *d_masks, long long n_cells
     }
 #undef HN_CASE
   check_launch("hanging-node kernel");
+}
+
+template <typename Number>
+void dg_copy(int degree, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, int apply_constraints, cudaStream_t st)
+{
+  if (n_cells == 0) return;
+  const unsigned grid = (unsigned)n_cells;
+#define DG_CASE(N)                                                                                                              \
+  case N - 1:                                                                                                                   \
+    dg_copy_kernel<N, Number><<<grid, N * N, 0, st>>>((Number *)dst, (const Number *)src, d_masks, n_cells, apply_constraints); \
+    break;
+  switch (degree)
+    {
+      DG_CASE(2) DG_CASE(3) DG_CASE(4) DG_CASE(5) DG_CASE(6) DG_CASE(7) DG_CASE(8) DG_CASE(9)
+      default: throw std::runtime_error("unsupported degree");
+    }
+#undef DG_CASE
+  check_launch("DG copy kernel");
 }
 
 template <typename Number>
@@ -209,6 +260,17 @@ void run_hn_only(int degree, int number, void *values, const uint8_t *d_masks, l
     hn_only<double>(degree, values, d_masks, n_cells, transpose, stream);
   else
     hn_only<float>(degree, values, d_masks, n_cells, transpose, stream);
+}
+
+void run_dg_copy(int degree, int number, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, int apply_constraints, cudaStream_t stream)
+{
+  int device = 0;
+  cudaGetDevice(&device);
+  ensure_shape_tables(device);
+  if (number == 0)
+    dg_copy<double>(degree, dst, src, d_masks, n_cells, apply_constraints, stream);
+  else
+    dg_copy<float>(degree, dst, src, d_masks, n_cells, apply_constraints, stream);
 }
 
 double run_fma_bench(int number, int iters)

@@ -142,6 +142,7 @@ struct BulkParams
   void *dst;
   long long batch_begin, batch_end; // whole warp batches (cpw cells each)
   int apply_constraints;
+  int hn_mask_strategy; // every warp takes the interpolation passes
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(BulkCfg<n, Number>::warps * 32, OCC) bulk_cell
         if (g[r] != bulk_invalid) A[ec * B::Ss + B::LVoff + (e - ec * B::lv)] = v[r];
       }
   }
-  const bool any_hn = __any_sync(0xffffffffu, mask != 0u);
+  const bool any_hn = p.hn_mask_strategy || __any_sync(0xffffffffu, mask != 0u);
   unsigned hn_face, hn_edge, hn_cb;
   decode_mask_kernel_axes(mask, hn_face, hn_edge, hn_cb);
   __syncwarp();
@@ -392,6 +393,7 @@ void launch_bulk_impl(const BulkLayout &L, const CellLoopParams &cp, int device,
   p.batch_begin       = cp.cell_begin / Cfg::cpw;
   p.batch_end         = cp.cell_end / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
+  p.hn_mask_strategy  = cp.hn_mask_strategy && cp.apply_constraints;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + B::warps - 1) / B::warps);

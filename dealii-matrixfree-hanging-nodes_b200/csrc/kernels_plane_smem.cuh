@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_sme
 
   const unsigned mask = (valid && p.apply_constraints) ? p.masks[cell] : 0u;
   const Number h      = valid ? static_cast<const Number *>(p.h)[cell] : Number(0);
-  const bool any_hn   = __any_sync(0xffffffffu, mask != 0u);
+  const bool any_hn   = p.hn_mask_strategy || __any_sync(0xffffffffu, mask != 0u);
   unsigned hn_face, hn_edge, hn_cb;
   decode_mask_kernel_axes(mask, hn_face, hn_edge, hn_cb);
 
@@ -227,6 +227,7 @@ void launch_plane_smem(const PlaneLayout &L, const CellLoopParams &cp, int devic
   p.batch_begin       = cp.cell_begin / Cfg::cpw;
   p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
   p.apply_constraints = cp.apply_constraints;
+  p.hn_mask_strategy  = cp.hn_mask_strategy && cp.apply_constraints;
   p.n_owned           = peer ? peer->n_owned : 0;
   p.ghost_src         = peer ? peer->ghost_src : nullptr;
   p.ghost_dst         = peer ? peer->ghost_dst : nullptr;

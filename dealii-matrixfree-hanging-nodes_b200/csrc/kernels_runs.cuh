@@ -77,6 +77,7 @@ struct RunsParams
   long long batch_begin, batch_end, n_cells;
   int sr;
   int apply_constraints;
+  int hn_mask_strategy; // every warp takes the interpolation passes
 };
 
 // OCC = CTAs per SM the register allocation is limited for (4: 128, 5: 96, 6: 80 registers per thread)
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(RunsCfg<n, Number>::warps * 32, OCC) runs_cell
     }
   const int nov = (int)(hdr.z >> 16), nz = (int)(hdr.z & 0xffffu);
   for (int i = lane; i < nov; i += 32) A[__ldg(p.ov_pos + hdr.x + i)] = __ldg(src + __ldg(p.ov_idx + hdr.x + i));
-  const bool any_hn   = __any_sync(0xffffffffu, mask != 0u);
+  const bool any_hn   = p.hn_mask_strategy || __any_sync(0xffffffffu, mask != 0u);
   unsigned hn_face, hn_edge, hn_cb;
   decode_mask_kernel_axes(mask, hn_face, hn_edge, hn_cb);
   __syncwarp();
@@ -329,6 +330,7 @@ void launch_runs_impl(const RunsLayout &L, const CellLoopParams &cp, int device,
   p.batch_end         = (cp.cell_end + Cfg::cpw - 1) / Cfg::cpw;
   p.n_cells           = L.n_cells;
   p.apply_constraints = cp.apply_constraints;
+  p.hn_mask_strategy  = cp.hn_mask_strategy && cp.apply_constraints;
   const long long nb  = p.batch_end - p.batch_begin;
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + R::warps - 1) / R::warps);

@@ -127,6 +127,7 @@ struct Operator
   BaselineArrays baseline;      // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use)
   std::vector<long long> segments;
   long long launches = 0;
+  int hn_strategy = 0;    // MFHN_HN_BRANCH / MFHN_HN_MASK
   int vector_padding = 0; // valid entries behind n_owned + n_ghost in every vector (promise of the caller)
   void *d_stage_src[2] = {nullptr, nullptr}, *d_stage_dst[2] = {nullptr, nullptr}; // device staging of the host-vector entry point (2 slots)
 
@@ -286,6 +287,7 @@ void op_vmult_range(Operator &op, void *dst, const void *src, cudaStream_t strea
   p.cell_begin        = cb;
   p.cell_end          = ce;
   p.apply_constraints = op.apply_constraints;
+  p.hn_mask_strategy  = op.hn_strategy == MFHN_HN_MASK;
   int kernel          = resolve_kernel(op);
   if ((kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_RUNS) && (((uintptr_t)src | (uintptr_t)dst) & 15u))
     {
@@ -702,6 +704,24 @@ int mfhn_op_apply_hn(mfhn_op h, void *values, int transpose, void *stream)
     Operator &op = *reinterpret_cast<Operator *>(h);
     CUDA_CHECK(cudaSetDevice(op.device));
     run_hn_only(op.degree, op.number, values, op.d_masks, op.n_cells, transpose, static_cast<cudaStream_t>(stream));
+    ++op.launches;
+  });
+}
+int mfhn_op_set_hn_strategy(mfhn_op h, int strategy)
+{
+  return guard([&] {
+    if (!h) throw InvalidArgument("null argument");
+    if (strategy != MFHN_HN_BRANCH && strategy != MFHN_HN_MASK) throw InvalidArgument("unknown hanging-node strategy");
+    reinterpret_cast<Operator *>(h)->hn_strategy = strategy;
+  });
+}
+int mfhn_op_dg_copy(mfhn_op h, void *dst_cells, const void *src_cells, void *stream)
+{
+  return guard([&] {
+    if (!h || !dst_cells || !src_cells) throw InvalidArgument("null argument");
+    Operator &op = *reinterpret_cast<Operator *>(h);
+    CUDA_CHECK(cudaSetDevice(op.device));
+    run_dg_copy(op.degree, op.number, dst_cells, src_cells, op.d_masks, op.n_cells, op.apply_constraints, static_cast<cudaStream_t>(stream));
     ++op.launches;
   });
 }

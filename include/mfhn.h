@@ -237,6 +237,18 @@ int mfhn_op_set_kernel(mfhn_op op, int kernel);
  * [n_cells][(k+1)^3]): FEEvaluationHangingNodesFactory::apply
  * (benchmark_00_likwid.cc:56-59). */
 int mfhn_op_apply_hn(mfhn_op op, void *cell_values, int transpose, void *cuda_stream);
+/* "DG (C)" stage of the reference's decomposition (benchmark_01.cc:189-199; benchmark_01.h:617-677 with cell-local
+ * vectors): dst_cells += [interpolation^T interpolation] src_cells on [n_cells][(k+1)^3] device arrays, no
+ * quadrature-point work; constraints as set by mfhn_op_set_apply_constraints. */
+int mfhn_op_dg_copy(mfhn_op op, void *dst_cells, const void *src_cells, void *cuda_stream);
+/* Hanging-node strategy of the fused cell kernels (analogues of the reference's index / sorted / mask vectorisation
+ * types, benchmark_01.cc:70-116): MFHN_HN_BRANCH (default) = a warp takes the interpolation passes only if one of its
+ * cells is constrained (with the categorised cell order of mfhn_mf_create this is the "sorted" strategy, with plain
+ * Morton order the "index" strategy); MFHN_HN_MASK = every warp takes the passes, constrained lines are selected by
+ * per-lane predicates (no data-dependent branch, no dependence on the cell order). */
+#define MFHN_HN_BRANCH 0
+#define MFHN_HN_MASK 1
+int mfhn_op_set_hn_strategy(mfhn_op op, int strategy);
 
 /* Queries: algorithmic bytes / flops of one vmult, cell counts. */
 int mfhn_op_query(mfhn_op op, const char *what, double *value);

@@ -500,3 +500,43 @@ def test_general_per_quadrature_point_geometry(mfhn):
     Ab = operators.vmult_general(lo, b, G)
     live = ref != 0
     assert abs(b[live] @ y[live] - x[live] @ Ab[live]) < 1e-10 * abs(b[live] @ y[live])
+
+
+@pytest.mark.parametrize("k", [2, 4, 6])
+def test_hn_mask_strategy_and_dg_copy(mfhn, k):
+    """(i) MFHN_HN_MASK (every warp takes the interpolation passes, per-lane predicates: the reference's "mask"
+    vectorisation type, benchmark_01.cc:70-116) gives the same vmult as the default branch strategy, for every fast
+    kernel.  (ii) DG (C) stage (benchmark_01.cc:189-199): dst += W^T W src on cell-local values against the oracle's
+    interpolation matrices."""
+    import torch
+
+    geo, L = ("annulus", 5) if k <= 4 else ("quadrant", 4)
+    dh, mf, lay = _case(mfhn, geo, L, "serial", k)
+    x = _src(lay, "random")
+    ref = operators.vmult_fast(lay, x)
+    op = mfhn.LaplaceOperator(mf)
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.copy_(torch.from_numpy(x))
+    for kern in ("plane", "bulk", "runs"):
+        try:
+            op.set_kernel(kern)
+            op.set_hn_strategy("mask")
+            op.vmult(dst, src, zero_dst=True)
+        except mfhn.MfhnError:
+            continue
+        finally:
+            op.set_hn_strategy("branch")
+        y = dst.cpu().numpy()
+        assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12, (k, kern)
+    # DG (C): cell-local values, constraints on / off
+    n, n3 = k + 1, (k + 1) ** 3
+    rng = np.random.default_rng(3)
+    v = rng.uniform(-1, 1, (mf.n_cells, n3))
+    kinds = np.array([dofs.decompress(int(m)) for m in mf.masks], dtype=np.uint16)
+    want = operators.hn_apply(operators.hn_apply(v.reshape(-1, n, n, n).copy(), kinds, k, False), kinds, k, True).reshape(-1, n3)
+    sv, dv = torch.from_numpy(v).cuda().reshape(-1), torch.zeros(mf.n_cells * n3, dtype=torch.float64, device="cuda")
+    op.dg_copy(dv, sv)
+    assert np.abs(dv.cpu().numpy().reshape(-1, n3) - want).max() < 1e-12
+    op.set_apply_constraints(False)
+    op.dg_copy(dv, sv)
+    assert np.abs(dv.cpu().numpy().reshape(-1, n3) - want - v).max() < 1e-12
