@@ -266,3 +266,35 @@ def cg_benchmark(mfhn, torch, dist, args, L, rank, world):
             "config": {"workload": f"{args.geometry} L={L}, FE_Q({args.degree}), {args.number}, CG + point-Jacobi", "n_dofs": int(n_dofs),
                        "n_cells": int(prob["n_cells_global"]), "kernel": prob["kernel_name"], "partition": prob["partition"],
                        "tolerance": args.cg_tol, "max_iterations": args.cg_iterations}}
+
+
+def high_order_geometry(mfhn, tria, mf, degree, amplitude=1e-6):
+    """Per-quadrature-point coefficients JxW J^-1 J^-T ([cell][6][(k+1)^3], xx xy xz yy yz zz) of the reference's
+    TestHighOrderMapping (benchmark_01.h:225-242): the Cartesian mesh displaced by amplitude * sin(pi x_d) in every
+    coordinate direction (a smooth deformation resolved by the high-order mapping), evaluated at the Gauss points."""
+    k, n = degree, degree + 1
+    q, w = np.polynomial.legendre.leggauss(n)
+    q, w = 0.5 * (q + 1.0), 0.5 * w
+    w3 = (w[:, None, None] * w[None, :, None] * w[None, None, :]).ravel()
+    cells = tria.cells()[mf.cell_ids]  # (level, i, j, k)
+    h = mf.h
+    org = -1.0 + cells[:, 1:4] * h[:, None]
+    qq = (np.tile(q, n * n), np.tile(np.repeat(q, n), n), np.repeat(q, n * n))
+    G = np.zeros((mf.n_cells, 6, n ** 3))
+    chunk = 65536
+    for a in range(0, mf.n_cells, chunk):
+        b = min(a + chunk, mf.n_cells)
+        X = [org[a:b, d, None] + h[a:b, None] * qq[d][None, :] for d in range(3)]
+        # x_d = X_d + amplitude sin(pi X_d) sin(pi X_{d+1}): a full (non-diagonal) Jacobian
+        J = np.zeros((b - a, n ** 3, 3, 3))
+        for d in range(3):
+            e = (d + 1) % 3
+            J[..., d, d] = 1.0 + amplitude * np.pi * np.cos(np.pi * X[d]) * np.sin(np.pi * X[e])
+            J[..., d, e] = amplitude * np.pi * np.sin(np.pi * X[d]) * np.cos(np.pi * X[e])
+        J *= h[a:b, None, None, None]
+        det = np.linalg.det(J)
+        Ji = np.linalg.inv(J)
+        M = np.einsum("cqik,cqjk->cqij", Ji, Ji) * (det * w3[None, :])[..., None, None]
+        for c, (i, j) in enumerate(((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))):
+            G[a:b, c, :] = M[..., i, j]
+    return G

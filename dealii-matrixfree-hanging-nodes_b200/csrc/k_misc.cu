@@ -118,21 +118,24 @@ __global__ void hn_only_kernel(Number *values, const uint8_t *masks, long long n
 
 // "DG (C)" of the reference's stage decomposition (benchmark_01.cc:189-199, benchmark_01.h:617-677 with VectorType1):
 // every cell owns private DoFs, no quadrature-point work -- gather_plain [+ interpolation], [interpolation^T +]
-// scatter_plain, dst += values.  Cells without constraints skip shared memory altogether.
+// scatter_plain, dst += values.  Two kernels: a flat streaming pass over the entries of the unconstrained cells and one
+// block per constrained cell (list built at setup) for W^T W.
+template <typename Number>
+__global__ void __launch_bounds__(256) dg_copy_plain_kernel(Number *dst, const Number *src, const uint8_t *masks, const long long n_entries, const int n3,
+                                                             const int apply_constraints)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (long long)gridDim.x * blockDim.x)
+    if (!apply_constraints || masks[i / n3] == 0) dst[i] += src[i];
+}
 template <int n, typename Number>
-__global__ void dg_copy_kernel(Number *dst, const Number *src, const uint8_t *masks, long long n_cells, int apply_constraints)
+__global__ void dg_copy_hn_kernel(Number *dst, const Number *src, const uint8_t *masks, const int32_t *hn_cells)
 {
   __shared__ Number s[n * n * n];
-  const long long cell = blockIdx.x;
+  const long long cell = hn_cells[blockIdx.x];
   const int l          = threadIdx.x;
-  const unsigned mask  = apply_constraints ? masks[cell] : 0u;
+  const unsigned mask  = masks[cell];
   const Number *g      = src + cell * (n * n * n);
   Number *o            = dst + cell * (n * n * n);
-  if (mask == 0u)
-    {
-      for (int z = 0; z < n; ++z) o[l + n * n * z] += g[l + n * n * z];
-      return;
-    }
   for (int z = 0; z < n; ++z) s[l + n * n * z] = g[l + n * n * z];
   __syncthreads();
   hn_passes_block<n>(s, l, mask, false);
@@ -159,13 +162,20 @@ void hn_only(int degree, void *values, const uint8_t *d_masks, long long n_cells
 }
 
 template <typename Number>
-void dg_copy(int degree, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, int apply_constraints, cudaStream_t st)
+void dg_copy(int degree, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, const int32_t *d_hn_cells, long long n_hn,
+             int apply_constraints, cudaStream_t st)
 {
   if (n_cells == 0) return;
-  const unsigned grid = (unsigned)n_cells;
-#define DG_CASE(N)                                                                                                              \
-  case N - 1:                                                                                                                   \
-    dg_copy_kernel<N, Number><<<grid, N * N, 0, st>>>((Number *)dst, (const Number *)src, d_masks, n_cells, apply_constraints); \
+  const int n3 = (degree + 1) * (degree + 1) * (degree + 1);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  dg_copy_plain_kernel<Number><<<sms * 16, 256, 0, st>>>((Number *)dst, (const Number *)src, d_masks, n_cells * n3, n3, apply_constraints);
+  check_launch("DG copy kernel");
+  if (!apply_constraints || n_hn == 0) return;
+#define DG_CASE(N)                                                                                                \
+  case N - 1:                                                                                                     \
+    dg_copy_hn_kernel<N, Number><<<(unsigned)n_hn, N * N, 0, st>>>((Number *)dst, (const Number *)src, d_masks, d_hn_cells); \
     break;
   switch (degree)
     {
@@ -173,7 +183,7 @@ void dg_copy(int degree, void *dst, const void *src, const uint8_t *d_masks, lon
       default: throw std::runtime_error("unsupported degree");
     }
 #undef DG_CASE
-  check_launch("DG copy kernel");
+  check_launch("DG copy kernel (constrained cells)");
 }
 
 template <typename Number>
@@ -262,15 +272,16 @@ void run_hn_only(int degree, int number, void *values, const uint8_t *d_masks, l
     hn_only<float>(degree, values, d_masks, n_cells, transpose, stream);
 }
 
-void run_dg_copy(int degree, int number, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, int apply_constraints, cudaStream_t stream)
+void run_dg_copy(int degree, int number, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, const int32_t *d_hn_cells, long long n_hn,
+                 int apply_constraints, cudaStream_t stream)
 {
   int device = 0;
   cudaGetDevice(&device);
   ensure_shape_tables(device);
   if (number == 0)
-    dg_copy<double>(degree, dst, src, d_masks, n_cells, apply_constraints, stream);
+    dg_copy<double>(degree, dst, src, d_masks, n_cells, d_hn_cells, n_hn, apply_constraints, stream);
   else
-    dg_copy<float>(degree, dst, src, d_masks, n_cells, apply_constraints, stream);
+    dg_copy<float>(degree, dst, src, d_masks, n_cells, d_hn_cells, n_hn, apply_constraints, stream);
 }
 
 double run_fma_bench(int number, int iters)

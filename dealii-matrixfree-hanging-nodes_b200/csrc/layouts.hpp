@@ -139,7 +139,8 @@ long long runs_verify(const RunsHostLayout &L, int number, const uint32_t *idx, 
 void run_baseline(int degree, int number, BaselineArrays &arrays, const uint32_t *d_idx, const void *d_h, long long n_cells, const CellLoopParams &p,
                   int device, cudaStream_t stream);
 void run_hn_only(int degree, int number, void *values, const uint8_t *d_masks, long long n_cells, int transpose, cudaStream_t stream);
-void run_dg_copy(int degree, int number, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, int apply_constraints, cudaStream_t stream);
+void run_dg_copy(int degree, int number, void *dst, const void *src, const uint8_t *d_masks, long long n_cells, const int32_t *d_hn_cells, long long n_hn,
+                 int apply_constraints, cudaStream_t stream);
 double run_fma_bench(int number, int iters);
 void run_pack(int number, void *buffer, const void *vec, const int32_t *idx, long long n, cudaStream_t stream);
 void run_unpack_add(int number, void *vec, const void *buffer, const int32_t *idx, long long n, bool atomic, cudaStream_t stream);

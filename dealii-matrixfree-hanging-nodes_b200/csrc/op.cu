@@ -120,6 +120,7 @@ struct Operator
   long long n_cells = 0, n_owned = 0, n_ghost = 0, n_cells_hn = 0;
   uint32_t *d_idx = nullptr;    // reference layout [cell][lexicographic]
   uint8_t *d_masks = nullptr;
+  int32_t *d_hn_cells = nullptr; // cells with a non-zero mask, ascending (DG (C) stage)
   void *d_geom = nullptr;       // Number h[cell], Number G[cell][6] or Number G[cell][6][q]
   PlaneLayout plane;            // warp-interleaved layout of the plane kernels
   BulkLayout bulk;              // block descriptors of the bulk-copy kernel (degrees 3..5)
@@ -135,6 +136,7 @@ struct Operator
   {
     cudaFree(d_idx);
     cudaFree(d_masks);
+    cudaFree(d_hn_cells);
     cudaFree(d_geom);
     for (int i = 0; i < 2; ++i)
       {
@@ -327,12 +329,16 @@ Operator *op_create(const mfhn_op_desc &d)
   const long long nvec  = d.n_owned + d.n_ghost;
   for (long long i = 0; i < d.n_cells * n3; ++i)
     if (d.dof_indices[i] >= (unsigned long long)nvec) throw InvalidArgument("dof index out of range");
+  if (d.n_cells > 0x7fffffffll) throw InvalidArgument("more than 2^31 cells on one rank");
+  std::vector<int32_t> hn_cells;
   for (long long c = 0; c < d.n_cells; ++c)
     {
       if (!check_kind(decompress_kind(d.masks[c])) || compress_kind(decompress_kind(d.masks[c])) != d.masks[c])
         throw InvalidArgument("invalid compressed constraint mask");
-      op->n_cells_hn += d.masks[c] != 0;
+      if (d.masks[c] != 0) hn_cells.push_back((int32_t)c);
     }
+  op->n_cells_hn = (long long)hn_cells.size();
+  op->d_hn_cells = to_device(hn_cells);
   CUDA_CHECK(cudaMalloc(&op->d_idx, std::max<size_t>(1, d.n_cells * n3) * sizeof(uint32_t)));
   CUDA_CHECK(cudaMemcpy(op->d_idx, d.dof_indices, d.n_cells * n3 * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMalloc(&op->d_masks, std::max<size_t>(1, d.n_cells)));
@@ -721,8 +727,9 @@ int mfhn_op_dg_copy(mfhn_op h, void *dst_cells, const void *src_cells, void *str
     if (!h || !dst_cells || !src_cells) throw InvalidArgument("null argument");
     Operator &op = *reinterpret_cast<Operator *>(h);
     CUDA_CHECK(cudaSetDevice(op.device));
-    run_dg_copy(op.degree, op.number, dst_cells, src_cells, op.d_masks, op.n_cells, op.apply_constraints, static_cast<cudaStream_t>(stream));
-    ++op.launches;
+    run_dg_copy(op.degree, op.number, dst_cells, src_cells, op.d_masks, op.n_cells, op.d_hn_cells, op.n_cells_hn, op.apply_constraints,
+                static_cast<cudaStream_t>(stream));
+    op.launches += 1 + (op.apply_constraints && op.n_cells_hn > 0);
   });
 }
 int mfhn_op_query(mfhn_op h, const char *what, double *value)

@@ -8,15 +8,15 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-constexpr int n = 8, cells_per_cta = 8, threads = 256;
+constexpr int n = 8, ls = 9, cells_per_cta = 8, threads = 256; // ls: line stride, padded against bank conflicts
 __constant__ double Tm[n * n];
 
 template <int MODE>
 __global__ void __launch_bounds__(threads) sweep(double *out, int iters)
 {
-  __shared__ double A[cells_per_cta][n * n * n + 8]; // [cell][line][entry], lines contiguous
+  __shared__ double A[cells_per_cta][n * n * ls]; // [cell][line][entry], line stride ls
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < cells_per_cta * (n * n * n + 8); i += threads) (&A[0][0])[i] = 1.0 + 1e-3 * (i % 17);
+  for (int i = tid; i < cells_per_cta * n * n * ls; i += threads) (&A[0][0])[i] = 1.0 + 1e-3 * (i % 17);
   __syncthreads();
   for (int it = 0; it < iters; ++it)
     {
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(threads) sweep(double *out, int iters)
           for (int r = 0; r < 2; ++r)
             {
               const int l = tid + r * threads, c = l / (n * n), q = l % (n * n);
-              double *line = &A[c][q * n];
+              double *line = &A[c][q * ls];
               double x[n], y[n];
 #pragma unroll
               for (int i = 0; i < n; ++i) x[i] = line[i];
@@ -79,22 +79,22 @@ __global__ void __launch_bounds__(threads) sweep(double *out, int iters)
 #pragma unroll
           for (int blk = 0; blk < n; ++blk)
             {
-              double *X = &A[c][blk * n * n]; // 8 lines of 8 entries: X[l * n + j]
-              const double b0 = X[(lane / 4) * n + lane % 4], b1 = X[(lane / 4) * n + 4 + lane % 4];
+              double *X = &A[c][blk * n * ls]; // 8 lines of 8 entries: X[l * ls + j]
+              const double b0 = X[(lane / 4) * ls + lane % 4], b1 = X[(lane / 4) * ls + 4 + lane % 4];
               double d0 = 0.0, d1 = 0.0;
               asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a0), "d"(b0));
               asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a1), "d"(b1));
               __syncwarp();
               // D[i = lane / 4][l = 2 (lane % 4) + {0, 1}] -> line l, entry i
-              X[(2 * (lane % 4)) * n + lane / 4]     = d0;
-              X[(2 * (lane % 4) + 1) * n + lane / 4] = d1;
+              X[(2 * (lane % 4)) * ls + lane / 4]     = d0;
+              X[(2 * (lane % 4) + 1) * ls + lane / 4] = d1;
               __syncwarp();
             }
         }
       __syncthreads();
     }
   double s = 0;
-  for (int i = tid; i < cells_per_cta * n * n * n; i += threads) s += A[i / (n * n * n)][i % (n * n * n)];
+  for (int i = tid; i < cells_per_cta * n * n * ls; i += threads) s += (&A[0][0])[i];
   if (s == -1.0) out[0] = s;
 }
 
