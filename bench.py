@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the compact degree sweep (degrees 1..8, double + float) of the default line")
     ap.add_argument("--no-weak", action="store_true", help="8 GPUs: skip the extra weak-scaling run on the next finer mesh")
     ap.add_argument("--stages", action="store_true", help="the reference's DG (SC) / CG (SC) decomposition and eta (benchmark_01.cc:189-220)")
+    ap.add_argument("--mapping", default="cartesian", choices=["cartesian", "high-order"],
+                    help="high-order: per-quadrature-point geometry of the reference's TestHighOrderMapping (benchmark_01.h:225-242), q-point kernel, own byte model")
     ap.add_argument("--cg", action="store_true", help="BASELINE.json config 5: CG + point-Jacobi solve (degree 6 unless --degree is given), time per iteration split")
     ap.add_argument("--cg-iterations", type=int, default=100)
     ap.add_argument("--cg-tol", type=float, default=1e-8)
@@ -61,6 +63,8 @@ def parse():
     ap.add_argument("--minimal", action="store_true", help="timed loop only (for profiler runs)")
     ap.add_argument("--graph", action="store_true", help="partitioned runs: replay a CUDA graph of one vmult (experimental: the capture of the NCCL p2p groups hung on this pool, so it is off by default)")
     args = ap.parse_args()
+    if args.mapping == "high-order" and (args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1):
+        ap.error("--mapping high-order is a one-GPU mode")
     if args.degree is None:
         args.degree = 6 if args.cg else 4
     return args
@@ -125,6 +129,8 @@ def default_refinements(args):
     (142.8 M DoFs at k=4), L=8 for k >= 5.  The 8-GPU weak-scaling run on L+1 is an extra key of the N=8 line."""
     if args.refinements is not None:
         return args.refinements
+    if args.mapping == "high-order":
+        return 8 if args.degree <= 4 else 7  # 6 s (k+1)^3 bytes of coefficients per cell: 1.6 GB at L=8, k=4
     if args.geometry == "annulus":
         return 9 if args.degree <= 4 else 8
     return 8 if args.degree <= 4 else 7
@@ -223,7 +229,8 @@ def run():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     L = default_refinements(args)
-    workload = f"{args.geometry} L={L} (p4est-balanced octree on hyper_cube(-1,1)^3), FE_Q({args.degree}), {args.number}, Cartesian MappingQ1"
+    mapping = "Cartesian MappingQ1" if args.mapping == "cartesian" else "high-order mapping (1e-6 sin displacement, per-quadrature-point JxW J^-1 J^-T, benchmark_01.h:225-242)"
+    workload = f"{args.geometry} L={L} (p4est-balanced octree on hyper_cube(-1,1)^3), FE_Q({args.degree}), {args.number}, {mapping}"
 
     mfhn = importlib.import_module(PKG)
 
@@ -361,7 +368,9 @@ def run():
             traffic = entry
     out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "algorithmic_bytes_without_dst_read": b_alg_plain,
-                       "bytes_note": "3 s n_dofs + n_cells (4 (k+1)^3 + 1 + 3 s): src read, dst read+write (accumulating vmult), uint32 indices, mask, Cartesian geometry",
+                       "bytes_note": "3 s n_dofs + n_cells (4 (k+1)^3 + 1 + 3 s): src read, dst read+write (accumulating vmult), uint32 indices, mask, Cartesian geometry"
+                                     if args.mapping == "cartesian" else
+                                     "3 s n_dofs + n_cells (4 (k+1)^3 + 1 + 6 s (k+1)^3): vectors, indices, mask, six coefficients per quadrature point",
                        "kernel_ms_min_avg_max": [float(per.min()), float(per.mean()), float(per.max())],
                        "algorithmic_flops_per_launch": flops}
     out["clocks"] = clocks.summary()
@@ -382,6 +391,7 @@ def run():
         n_hn, n_all = int(prob["n_cells_hn_global"]), int(prob["n_cells_global"])
         t_n, t_hn = float(np.mean(per_nc)), float(np.mean(per))
         out["eta5"] = max((t_hn / (t_n / n_all) - (n_all - n_hn)) / n_hn, 1.0) if n_hn else 1.0
+    if rank == 0 and world == 1 and not args.minimal and args.mapping == "cartesian":
         # the other kernels on the same problem, for the record
         variants = {}
         for kname in ("plane", "bulk", "runs", "qpoint", "separable", "baseline"):
@@ -508,11 +518,11 @@ def run():
                                   "upload / download streams beside the vmult stream; bytes are per rank")
             del hbuf
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.minimal:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.minimal and args.mapping == "cartesian":
         cb, _, _ = run_cpu(args, mf, args.degree, 5)
         out["cpu_baseline"] = cb
 
-    if world == 1 and rank == 0 and not args.minimal and (args.sweep or not args.no_sweep):
+    if world == 1 and rank == 0 and not args.minimal and (args.sweep or not args.no_sweep) and args.mapping == "cartesian":
         from bench_dist import degree_sweep
 
         del src, dst

@@ -21,7 +21,9 @@ def build_problem(mfhn, args, L, rank, world):
     if world == 1:
         dh = mfhn.DoFHandler(tria, args.degree)
         mf = mfhn.MatrixFree(dh)
-        op = mfhn.LaplaceOperator(mf, number=args.number, kernel=args.kernel)
+        geometry = high_order_geometry(mfhn, tria, mf, args.degree) if getattr(args, "mapping", "cartesian") == "high-order" else None
+        op = mfhn.LaplaceOperator(mf, number=args.number, kernel=args.kernel, geometry=geometry)
+        del geometry
         comm = None
         partition = "1 GPU, whole mesh"
         launches = 1

@@ -79,8 +79,12 @@ struct GenericCfg
   static constexpr int nx  = n | 1;                 // padded row length (odd: conflict-free x sweeps)
   static constexpr int cs  = n * n * nx;            // array stride per cell
   static constexpr int tpc = n * n;                 // threads per cell
-  static constexpr int cpb = (256 / tpc) > 0 ? (256 / tpc) : 1;
-  static constexpr int threads = cpb * tpc;
+  // n^2 <= 32: the threads of a cell sit in ONE warp (32 / n^2 cells per warp, the other lanes leave at once), so the
+  // barriers between the sweeps are __syncwarp over those lanes instead of block barriers over 10 unrelated cells
+  static constexpr int wc  = tpc <= 32 ? 32 / tpc : 0; // cells per warp (0: block mode)
+  static constexpr unsigned lanes = wc ? (wc * tpc == 32 ? 0xffffffffu : (1u << (wc * tpc)) - 1u) : 0u;
+  static constexpr int cpb = wc ? 8 * wc : ((256 / tpc) > 0 ? (256 / tpc) : 1);
+  static constexpr int threads = wc ? 256 : cpb * tpc;
 };
 
 template <int VARIANT>
@@ -103,8 +107,15 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
   Number *smem = reinterpret_cast<Number *>(smem_raw);
 
   const int tid  = threadIdx.x;
-  const int cib  = tid / Cfg::tpc;
-  const int l    = tid % Cfg::tpc;
+  if (Cfg::wc && (tid & 31) >= Cfg::wc * Cfg::tpc) return; // lanes beyond the warp's cells
+  const int cib  = Cfg::wc ? (tid >> 5) * Cfg::wc + (tid & 31) / Cfg::tpc : tid / Cfg::tpc;
+  const int l    = Cfg::wc ? (tid & 31) % Cfg::tpc : tid % Cfg::tpc;
+  auto cell_sync = [&]() {
+    if (Cfg::wc)
+      __syncwarp(Cfg::lanes);
+    else
+      __syncthreads();
+  };
   const int a    = l % n;
   const int b    = l / n;
   const long long cell = p.cell_begin + (long long)blockIdx.x * Cfg::cpb + cib;
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
   {
   if (DIAG)
     {
-      __syncthreads();
+      cell_sync();
 #pragma unroll
       for (int z = 0; z < n; ++z) A0[bz + z * sz] = (l + n * n * z == unit) ? Number(1) : Number(0);
     }
@@ -142,17 +153,17 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
 #pragma unroll
       for (int z = 0; z < n; ++z) A0[bz + z * sz] = src[gidx[z]];
     }
-  const bool any_hn = __syncthreads_or(mask != 0);
+  const bool any_hn = Cfg::wc ? __any_sync(Cfg::lanes, mask != 0) : __syncthreads_or(mask != 0);
   unsigned face = 0, edge = 0, childbits = 0;
   decode_mask(mask, face, edge, childbits);
   if (any_hn)
     {
       if (mask) hn_pass_line<n, false>(A0 + bx, sx, 0, a, b, face, edge, childbits);
-      __syncthreads();
+      cell_sync();
       if (mask) hn_pass_line<n, false>(A0 + by, sy, 1, a, b, face, edge, childbits);
-      __syncthreads();
+      cell_sync();
       if (mask) hn_pass_line<n, false>(A0 + bz, sz, 2, a, b, face, edge, childbits);
-      __syncthreads();
+      cell_sync();
     }
 
   Number u[n], v[n], w[n];
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
       mat_vec<n, T_K, false>(u, w);
       store_line<n>(A0 + bx, sx, v);
       store_line<n>(A1 + bx, sx, w);
-      __syncthreads();
+      cell_sync();
       // y: a = M p, b = M q + K p
       load_line<n>(A0 + by, sy, u);
       load_line<n>(A1 + by, sy, v);
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
       mat_vec<n, T_M, false>(u, v); // M p
       store_line<n>(A0 + by, sy, v);
       store_line<n>(A1 + by, sy, w);
-      __syncthreads();
+      cell_sync();
       // z: r = h (M b + K a)
       load_line<n>(A0 + bz, sz, u);
       load_line<n>(A1 + bz, sz, v);
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
 #pragma unroll
       for (int i = 0; i < n; ++i) w[i] = h * (w[i] + v[i]);
       store_line<n>(A0 + bz, sz, w);
-      __syncthreads();
+      cell_sync();
     }
   else
     {
@@ -193,15 +204,15 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
       load_line<n>(A0 + bx, sx, u);
       mat_vec<n, T_S, false>(u, v);
       store_line<n>(A0 + bx, sx, v);
-      __syncthreads();
+      cell_sync();
       load_line<n>(A0 + by, sy, u);
       mat_vec<n, T_S, false>(u, v);
       store_line<n>(A0 + by, sy, v);
-      __syncthreads();
+      cell_sync();
       load_line<n>(A0 + bz, sz, u);
       mat_vec<n, T_S, false>(u, v);
       store_line<n>(A0 + bz, sz, v);
-      __syncthreads();
+      cell_sync();
       if (VARIANT == GV_QPOINT_CARTESIAN)
         {
           // gradient, q-point factor w_q * h (Cartesian: J^-1 J^-T detJ = h), integrate; direction by direction
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
           for (int i = 0; i < n; ++i) v[i] *= wq[i] * fac;
           mat_vec<n, T_DC, true>(v, w);
           store_line<n>(A1 + bx, sx, w);
-          __syncthreads();
+          cell_sync();
           // y
           load_line<n>(A0 + by, sy, u);
           mat_vec<n, T_DC, false>(u, v);
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
 #pragma unroll
           for (int i = 0; i < n; ++i) w[i] += v[i];
           store_line<n>(A1 + by, sy, w);
-          __syncthreads();
+          cell_sync();
           // z
           load_line<n>(A0 + bz, sz, u);
           mat_vec<n, T_DC, false>(u, v);
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
 #pragma unroll
           for (int i = 0; i < n; ++i) w[i] += v[i];
           store_line<n>(A0 + bz, sz, w); // result back into A0
-          __syncthreads();
+          cell_sync();
         }
       else
         {
@@ -267,7 +278,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
           load_line<n>(A0 + bz, sz, u);
           mat_vec<n, T_DC, false>(u, v);
           store_line<n>(GZ + bz, sz, v);
-          __syncthreads();
+          cell_sync();
           // q-point operation on the z line of thread (x=a, y=b): g <- w_q * G g
           {
             Number wq[n];
@@ -301,49 +312,49 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
                 GZ[bz + z * sz] = ww * (G[2] * gx + G[4] * gy + G[5] * gz);
               }
           }
-          __syncthreads();
+          cell_sync();
           load_line<n>(GX + bx, sx, u);
           mat_vec<n, T_DC, true>(u, v);
           store_line<n>(A0 + bx, sx, v);
-          __syncthreads();
+          cell_sync();
           load_line<n>(GY + by, sy, u);
           mat_vec<n, T_DC, true>(u, v);
           load_line<n>(A0 + by, sy, w);
 #pragma unroll
           for (int i = 0; i < n; ++i) v[i] += w[i];
           store_line<n>(A0 + by, sy, v);
-          __syncthreads();
+          cell_sync();
           load_line<n>(GZ + bz, sz, u);
           mat_vec<n, T_DC, true>(u, v);
           load_line<n>(A0 + bz, sz, w);
 #pragma unroll
           for (int i = 0; i < n; ++i) v[i] += w[i];
           store_line<n>(A0 + bz, sz, v);
-          __syncthreads();
+          cell_sync();
         }
       // integrate: S^T in z, y, x
       load_line<n>(A0 + bz, sz, u);
       mat_vec<n, T_S, true>(u, v);
       store_line<n>(A0 + bz, sz, v);
-      __syncthreads();
+      cell_sync();
       load_line<n>(A0 + by, sy, u);
       mat_vec<n, T_S, true>(u, v);
       store_line<n>(A0 + by, sy, v);
-      __syncthreads();
+      cell_sync();
       load_line<n>(A0 + bx, sx, u);
       mat_vec<n, T_S, true>(u, v);
       store_line<n>(A0 + bx, sx, v);
-      __syncthreads();
+      cell_sync();
     }
 
   if (any_hn)
     {
       if (mask) hn_pass_line<n, true>(A0 + bx, sx, 0, a, b, face, edge, childbits);
-      __syncthreads();
+      cell_sync();
       if (mask) hn_pass_line<n, true>(A0 + by, sy, 1, a, b, face, edge, childbits);
-      __syncthreads();
+      cell_sync();
       if (mask) hn_pass_line<n, true>(A0 + bz, sz, 2, a, b, face, edge, childbits);
-      __syncthreads();
+      cell_sync();
     }
   if (valid)
     {
