@@ -458,6 +458,12 @@ void nccl_group(NcclApi &nccl, F &&f)
   NCCL_CHECK(nccl.GroupEnd());
 }
 
+// One partitioned vmult.  The whole exchange chain runs on the high-priority communication stream -- pack, import
+// (update_ghost_values), the boundary cells, compress (add), unpack -- while ONE launch covers all interior cells on the
+// caller's stream: the scatter is atomic, so the order in which interior cells, boundary cells and imported
+// contributions reach dst does not matter, and the chain (about 60 us at 8 ranks) hides behind the interior cells
+// instead of cutting their launch in two.  (MFHN_DIST_SPLIT=1 keeps the round-1 schedule: interior A | boundary |
+// interior B on the caller's stream, for comparison.)
 void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero_dst)
 {
   Operator &op  = *d.op;
@@ -465,49 +471,61 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   const size_t s = op.number == MFHN_F64 ? 8 : 4;
   char *dstb = static_cast<char *>(dst);
   char *srcb = static_cast<char *>(const_cast<void *>(src));
+  static const bool split = env_int("MFHN_DIST_SPLIT", 0) != 0;
+  cudaStream_t cs = d.comm_stream;
   if (zero_dst) CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)(op.n_owned + op.n_ghost) * s, main));
+  CUDA_CHECK(cudaEventRecord(d.ev[0], main)); // src is final, dst zeroed
+  CUDA_CHECK(cudaStreamWaitEvent(cs, d.ev[0], 0));
   // pack the entries the peers ghost
   if (d.n_import > 0)
     {
-      run_pack(op.number, d.d_send, src, d.d_import_idx, d.n_import, main);
+      run_pack(op.number, d.d_send, src, d.d_import_idx, d.n_import, cs);
       ++d.launches;
     }
-  CUDA_CHECK(cudaEventRecord(d.ev[0], main));
-  CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[0], 0));
   // owners -> ghosts (update_ghost_values)
   nccl_group(nccl, [&] {
     for (size_t i = 0; i < d.ghost_peers.size(); ++i)
       NCCL_CHECK(nccl.Recv(srcb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
-                           d.ghost_peers[i], d.comm, d.comm_stream));
+                           d.ghost_peers[i], d.comm, cs));
     for (size_t i = 0; i < d.import_peers.size(); ++i)
       NCCL_CHECK(nccl.Send(static_cast<char *>(d.d_send) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
-                           d.import_peers[i], d.comm, d.comm_stream));
+                           d.import_peers[i], d.comm, cs));
   });
-  CUDA_CHECK(cudaEventRecord(d.ev[1], d.comm_stream));
-  if (d.seg[1] > d.seg[0]) op_vmult_range(op, dst, src, main, d.seg[0], d.seg[1]); // interior A overlaps the import
-  CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[1], 0));
-  if (d.seg[3] > d.seg[2]) op_vmult_range(op, dst, src, main, d.seg[2], d.seg[3]); // boundary cells need the ghosts
+  cudaStream_t bs = cs; // stream of the boundary cells
+  if (split)
+    {
+      CUDA_CHECK(cudaEventRecord(d.ev[1], cs));
+      if (d.seg[1] > d.seg[0]) op_vmult_range(op, dst, src, main, d.seg[0], d.seg[1]); // interior A overlaps the import
+      CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[1], 0));
+      bs = main;
+    }
+  if (d.seg[3] > d.seg[2]) op_vmult_range(op, dst, src, bs, d.seg[2], d.seg[3]); // boundary cells need the ghosts
   // zero_out_ghost_values: the imported entries are scratch, a later use of src as dst must not send them to the owners
-  if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(srcb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
-  CUDA_CHECK(cudaEventRecord(d.ev[2], main));
-  CUDA_CHECK(cudaStreamWaitEvent(d.comm_stream, d.ev[2], 0));
+  if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(srcb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, bs));
+  if (split)
+    {
+      CUDA_CHECK(cudaEventRecord(d.ev[2], main));
+      CUDA_CHECK(cudaStreamWaitEvent(cs, d.ev[2], 0));
+    }
   // ghosts -> owners (compress, add)
   nccl_group(nccl, [&] {
     for (size_t i = 0; i < d.import_peers.size(); ++i)
       NCCL_CHECK(nccl.Recv(static_cast<char *>(d.d_recv) + (size_t)d.import_off[i] * s, (size_t)(d.import_off[i + 1] - d.import_off[i]) * s, 0,
-                           d.import_peers[i], d.comm, d.comm_stream));
+                           d.import_peers[i], d.comm, cs));
     for (size_t i = 0; i < d.ghost_peers.size(); ++i)
       NCCL_CHECK(nccl.Send(dstb + (size_t)(op.n_owned + d.ghost_begin[i]) * s, (size_t)(d.ghost_end[i] - d.ghost_begin[i]) * s, 0,
-                           d.ghost_peers[i], d.comm, d.comm_stream));
+                           d.ghost_peers[i], d.comm, cs));
   });
-  CUDA_CHECK(cudaEventRecord(d.ev[3], d.comm_stream));
-  if (d.seg[2] > d.seg[1]) op_vmult_range(op, dst, src, main, d.seg[1], d.seg[2]); // interior B overlaps the compress
-  CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
   if (d.n_import > 0)
     {
-      run_unpack_add(op.number, dst, d.d_recv, d.d_import_idx, d.n_import, true, main); // several peers may add to one entry
+      run_unpack_add(op.number, dst, d.d_recv, d.d_import_idx, d.n_import, true, cs); // atomic: interior cells add to dst at the same time
       ++d.launches;
     }
+  CUDA_CHECK(cudaEventRecord(d.ev[3], cs));
+  // interior cells: one launch beside the chain (split schedule: the second half)
+  const long long ib = split ? d.seg[1] : d.seg[0];
+  if (d.seg[2] > ib) op_vmult_range(op, dst, src, main, ib, d.seg[2]);
+  CUDA_CHECK(cudaStreamWaitEvent(main, d.ev[3], 0));
   if (op.n_ghost > 0) CUDA_CHECK(cudaMemsetAsync(dstb + (size_t)op.n_owned * s, 0, (size_t)op.n_ghost * s, main));
 }
 
