@@ -462,8 +462,11 @@ void nccl_group(NcclApi &nccl, F &&f)
 // (update_ghost_values), the boundary cells, compress (add), unpack -- while ONE launch covers all interior cells on the
 // caller's stream: the scatter is atomic, so the order in which interior cells, boundary cells and imported
 // contributions reach dst does not matter, and the chain (about 60 us at 8 ranks) hides behind the interior cells
-// instead of cutting their launch in two.  (MFHN_DIST_SPLIT=1 keeps the round-1 schedule: interior A | boundary |
-// interior B on the caller's stream, for comparison.)
+// instead of cutting their launch in two.  That holds for two ranks (measured 232.9 vs 223.0 GDoF/s).  With more peers
+// the second NCCL kernel (compress) is launched while the interior kernel fills every SM; its large CTAs find no room until
+// the interior cells are through (8 ranks: 544.6 vs 650.8 GDoF/s), so from three ranks on the interior cells are cut in
+// two launches -- interior A | boundary | interior B on the caller's stream -- and each NCCL kernel is launched in front
+// of one of them.  MFHN_DIST_SPLIT=0/1 forces either schedule.
 void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero_dst)
 {
   Operator &op  = *d.op;
@@ -471,7 +474,7 @@ void dist_vmult(Dist &d, void *dst, const void *src, cudaStream_t main, int zero
   const size_t s = op.number == MFHN_F64 ? 8 : 4;
   char *dstb = static_cast<char *>(dst);
   char *srcb = static_cast<char *>(const_cast<void *>(src));
-  static const bool split = env_int("MFHN_DIST_SPLIT", 0) != 0;
+  const bool split = env_int("MFHN_DIST_SPLIT", d.world > 2 ? 1 : 0) != 0;
   cudaStream_t cs = d.comm_stream;
   if (zero_dst) CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)(op.n_owned + op.n_ghost) * s, main));
   CUDA_CHECK(cudaEventRecord(d.ev[0], main)); // src is final, dst zeroed
