@@ -15,6 +15,10 @@
 #pragma once
 #include "kernels_plane.cuh"
 
+#ifndef MFHN_PLANE_SMEM_OCC7
+#define MFHN_PLANE_SMEM_OCC7 1
+#endif
+
 namespace mfhn
 {
 template <int n, typename Number>
@@ -25,11 +29,13 @@ struct PlaneSmemCfg
   static constexpr int warps = (cpw * cs * (int)sizeof(Number) > 20 * 1024) ? 2 : 4; // 2-warp CTAs pack the SM better when a warp needs > 20 KB
   static constexpr int smem  = warps * cpw * cs * (int)sizeof(Number);
   static constexpr int rows_in_flight = n <= 7 ? 4 : 3; // gather rows issued before the first use
+  // CTAs per SM the register allocation is limited for: at k = 6 shared memory leaves room for 5 CTAs (20 warps)
+  static constexpr int min_ctas = (n == 7 && sizeof(Number) == 8) ? MFHN_PLANE_SMEM_OCC7 : 1;
 };
 
 
 template <int n, typename Number, bool PEER = false>
-__global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32) plane_smem_kernel(const PlaneParams p)
+__global__ void __launch_bounds__(PlaneSmemCfg<n, Number>::warps * 32, PlaneSmemCfg<n, Number>::min_ctas) plane_smem_kernel(const PlaneParams p)
 {
   using Cfg = PlaneSmemCfg<n, Number>;
   constexpr int ps = Cfg::ps, cs = Cfg::cs, cpw = Cfg::cpw, RF = Cfg::rows_in_flight;
