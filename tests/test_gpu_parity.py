@@ -64,8 +64,14 @@ def test_vmult_matches_oracle_annulus(mfhn, k, kernel, number):
         y, _ = _run(mfhn, mf, x, number, kernel)
         err = np.abs(y - ref).max() / np.abs(ref).max()
         if number == "float" and kind == "sin":
+            # A src cancels by > 10^3 on this smooth input: ROUNDING THE INPUT to float alone (double arithmetic after
+            # that) already moves the result by `pert` ~ 1e-5 of its size, so no float evaluation can meet 1e-5 of
+            # |A src|; the kernel has to stay within 15 x that perturbation and within 1e-5 of the
+            # cancellation-free scale |A| |src|
+            pert = np.abs(operators.vmult_fast(lay, x.astype(np.float32).astype(np.float64)) - ref).max() / np.abs(ref).max()
             scale = np.abs(operators.vmult_abs_bound(lay, x)).max()
             assert np.abs(y - ref).max() / scale < TOL[number], (k, kernel, number, kind, err)
+            assert err < max(2e-5, 15 * pert), (k, kernel, number, kind, err, pert)
             assert err < 1e-4, (k, kernel, number, kind, err)
         else:
             assert err < TOL[number], (k, kernel, number, kind, err)
