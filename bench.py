@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--hn-weight", type=float, default=1.0, help="partition weight of cells with hanging nodes (benchmark_02.cc:15-37)")
     ap.add_argument("--sweep", action="store_true", help="degree sweep with L=10 for k=1,2 and all kernel variants (the default line carries the compact sweep)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the compact degree sweep (degrees 1..8, double + float) of the default line")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys cg_jacobi (config 5; N = 1 and 8) and high_order_mapping (N = 1) of the default line")
     ap.add_argument("--no-weak", action="store_true", help="8 GPUs: skip the extra weak-scaling run on the next finer mesh")
     ap.add_argument("--stages", action="store_true", help="the reference's DG (SC) / CG (SC) decomposition and eta (benchmark_01.cc:189-220)")
     ap.add_argument("--mapping", default="cartesian", choices=["cartesian", "high-order"],
@@ -536,6 +537,29 @@ def run():
         src = dst = None
         torch.cuda.empty_cache()
         out["stages"] = stage_benchmarks(mfhn, torch, args, L, time_vmult)
+
+    extras = not args.no_extras and not args.minimal and args.refinements is None and args.mapping == "cartesian" and args.degree == 4 and not args.stages
+    if extras and world in (1, 8):
+        # BASELINE.json config 5: CG + point-Jacobi at degree 6 (N=1: annulus L=8, N=8: annulus L=9, 477 M DoFs)
+        import copy
+
+        from bench_dist import cg_benchmark
+
+        a2 = copy.copy(args)
+        a2.degree, a2.cg_iterations = 6, 60
+        log("cg extra")
+        extras_keep = []
+        res = cg_benchmark(mfhn, torch, dist if world > 1 else None, a2, 8 if world == 1 else 9, rank, world, keep=extras_keep)
+        out["cg_jacobi"] = {k: res[k] for k in ("value", "unit", "iterations", "residual_reduction", "ms_per_iteration", "gdofs_per_iteration",
+                                                "vector_kernels_gbs", "config")}
+        if world == 1:
+            extras_keep.clear()
+            torch.cuda.empty_cache()
+    if extras and world == 1 and rank == 0:
+        from bench_dist import high_order_benchmark
+
+        log("high-order extra")
+        out["high_order_mapping"] = high_order_benchmark(mfhn, torch, args, time_vmult, peaks()[0])
 
     if world == 8 and not args.no_weak and not args.minimal and args.refinements is None:
         # weak scaling (BASELINE.json config 4): the next finer mesh on 8 GPUs (annulus L=10, k=4: 1.124 B DoFs, 140.5 M per GPU).

@@ -11,7 +11,7 @@ def _log(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
-KERNEL_NAMES = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch", 6: "bulk", 7: "runs"}
+KERNEL_NAMES = {1: "qpoint", 2: "separable", 3: "baseline", 4: "plane", 5: "patch", 6: "bulk", 7: "runs", 8: "qpoint_rows"}
 
 
 def build_problem(mfhn, args, L, rank, world):
@@ -183,6 +183,19 @@ def stage_benchmarks(mfhn, torch, args, L, time_vmult):
     op.set_apply_constraints(True)
     _, t5 = time_vmult(torch, op, dst, src, 10, 3)
     res.update(t4_ms=float(t4.mean()), t5_ms=float(t5.mean()), eta5=eta(float(t4.mean()), float(t5.mean())))
+    # CG (SC) with the general-purpose constraint algorithm (benchmark_01.cc:222-234: t6, t7, eta7).  Both algorithms on
+    # the SAME cell kernel (the q-point kernel): t6 without constraints, t7 constraint rows in gather / scatter,
+    # t5_qpoint the fast interpolation passes
+    op.set_kernel("qpoint")
+    op.set_apply_constraints(False)
+    _, t6 = time_vmult(torch, op, dst, src, 5, 2)
+    op.set_apply_constraints(True)
+    _, t5q = time_vmult(torch, op, dst, src, 5, 2)
+    op.set_kernel("qpoint_rows")
+    _, t7 = time_vmult(torch, op, dst, src, 5, 2)
+    res.update(t6_ms=float(t6.mean()), t7_ms=float(t7.mean()), t5_qpoint_ms=float(t5q.mean()), eta7=eta(float(t6.mean()), float(t7.mean())),
+               eta5_qpoint=eta(float(t6.mean()), float(t5q.mean())), constraint_row_entries=int(op.query("constraint_row_entries")))
+    op.set_kernel(args.kernel)
     # the interpolation alone
     vals = torch.ones(mf.n_cells * n3, dtype=src.dtype, device=src.device)
     for _ in range(3):
@@ -234,7 +247,7 @@ def stage_benchmarks(mfhn, torch, args, L, time_vmult):
     return res
 
 
-def cg_benchmark(mfhn, torch, dist, args, L, rank, world):
+def cg_benchmark(mfhn, torch, dist, args, L, rank, world, keep=None):
     """BASELINE.json config 5: conjugate gradients with point-Jacobi on the adaptive mesh (degree 6 by default), the whole
     iteration inside the library (mfhn_cg_solve: one vmult, two fused vector kernels, one batched 3-scalar all-reduce per
     iteration).  The right-hand side is A x* for a random x*, so the system is consistent.  Reports the device time per
@@ -256,6 +269,8 @@ def cg_benchmark(mfhn, torch, dist, args, L, rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot, mv, vec, ar = (float(v) / max(its, 1) for v in t.tolist())
+    if keep is not None:
+        keep.append((prob, op, mf, xs, b, x, inv))  # communicators stay alive until the process ends
     s = 8 if args.number == "double" else 4
     n_dofs = prob["n_dofs"]
     return {"metric": "cg_jacobi_time_per_iteration", "value": tot, "unit": "ms", "higher_is_better": False, "n_gpus": world,
@@ -268,6 +283,25 @@ def cg_benchmark(mfhn, torch, dist, args, L, rank, world):
             "config": {"workload": f"{args.geometry} L={L}, FE_Q({args.degree}), {args.number}, CG + point-Jacobi", "n_dofs": int(n_dofs),
                        "n_cells": int(prob["n_cells_global"]), "kernel": prob["kernel_name"], "partition": prob["partition"],
                        "tolerance": args.cg_tol, "max_iterations": args.cg_iterations}}
+
+
+def high_order_benchmark(mfhn, torch, args, time_vmult, hbm_peak, L=8):
+    """Per-quadrature-point geometry (TestHighOrderMapping, benchmark_01.h:225-242) through the q-point kernel on the
+    annulus mesh one level below the headline mesh (six coefficients per quadrature point: 1.6 GB at L=8, k=4)."""
+    tria = mfhn.Triangulation(args.geometry, L, "p4est")
+    dh = mfhn.DoFHandler(tria, args.degree)
+    mf = mfhn.MatrixFree(dh)
+    G = high_order_geometry(mfhn, tria, mf, args.degree)
+    op = mfhn.LaplaceOperator(mf, number=args.number, geometry=G)
+    del G
+    src, dst = op.initialize_dof_vector(), op.initialize_dof_vector()
+    src.copy_(torch.sin(1e-3 * torch.arange(src.numel(), device=src.device, dtype=torch.float64)).to(src.dtype))
+    _, per = time_vmult(torch, op, dst, src, 10, 3)
+    t = float(np.mean(per))
+    b = op.query("algorithmic_bytes_accumulate")
+    return {"workload": f"{args.geometry} L={L}, FE_Q({args.degree}), {args.number}, high-order mapping (per-quadrature-point JxW J^-1 J^-T)",
+            "n_dofs": dh.n_dofs(), "kernel": KERNEL_NAMES[int(op.query("kernel"))], "ms_per_step": t, "gdofs": dh.n_dofs() / (t * 1e-3) / 1e9,
+            "algorithmic_bytes_per_launch": b, "frac_hbm": b / (t * 1e-3) / 1e9 / hbm_peak}
 
 
 def high_order_geometry(mfhn, tria, mf, degree, amplitude=1e-6):

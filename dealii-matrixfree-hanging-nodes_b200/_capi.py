@@ -177,4 +177,4 @@ VECTOR_PADDING = 4  # MFHN_VECTOR_PADDING: spare entries behind every vector han
 SERIAL, P4EST = 0, 1
 GEOM_CARTESIAN, GEOM_AFFINE, GEOM_GENERAL = 0, 1, 2
 KERNEL_AUTO, KERNEL_QPOINT, KERNEL_SEPARABLE, KERNEL_BASELINE, KERNEL_PLANE, KERNEL_PATCH = 0, 1, 2, 3, 4, 5
-KERNELS = {"auto": 0, "qpoint": 1, "separable": 2, "baseline": 3, "plane": 4, "patch": 5, "bulk": 6, "runs": 7}
+KERNELS = {"auto": 0, "qpoint": 1, "separable": 2, "baseline": 3, "plane": 4, "patch": 5, "bulk": 6, "runs": 7, "qpoint_rows": 8}

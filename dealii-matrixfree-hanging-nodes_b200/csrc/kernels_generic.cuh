@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
   using Cfg        = GenericCfg<n>;
   constexpr int nx = Cfg::nx, cs = Cfg::cs, k = n - 1;
   constexpr int NA = generic_n_arrays<VARIANT>();
+  constexpr bool ROWS = VARIANT == GV_QPOINT_ROWS; // general-purpose constraint algorithm around the Cartesian q-point sequence
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Number *smem = reinterpret_cast<Number *>(smem_raw);
 
@@ -137,8 +138,12 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
       const uint32_t *ip = p.idx + cell * (long long)(n * n * n) + l;
 #pragma unroll
       for (int z = 0; z < n; ++z) gidx[z] = ip[z * n * n];
-      if (p.apply_constraints) mask = p.masks[cell];
+      if (p.apply_constraints && !ROWS) mask = p.masks[cell];
     }
+  // ROWS: constrained cells gather / scatter through the weighted rows of their mask's interpolation matrix
+  const int row_kind = (ROWS && valid && p.apply_constraints) ? p.row_kind[cell] : 0;
+  const uint32_t *cell_idx = p.idx + cell * (long long)(n * n * n);
+  const int32_t *row_ptr   = ROWS ? p.row_ptr + (long long)(row_kind > 0 ? row_kind - 1 : 0) * (n * n * n + 1) : nullptr;
 #pragma unroll 1
   for (int unit = 0; unit < (DIAG ? n * n * n : 1); ++unit)
   {
@@ -150,8 +155,23 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
     }
   else if (valid)
     {
+      if (ROWS && row_kind > 0)
+        {
+          const Number *rv = static_cast<const Number *>(p.row_val);
+#pragma unroll 1
+          for (int z = 0; z < n; ++z)
+            {
+              const int i = l + n * n * z;
+              Number s    = Number(0);
+              for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) s += rv[e] * src[cell_idx[p.row_col[e]]];
+              A0[bz + z * sz] = s;
+            }
+        }
+      else
+        {
 #pragma unroll
-      for (int z = 0; z < n; ++z) A0[bz + z * sz] = src[gidx[z]];
+          for (int z = 0; z < n; ++z) A0[bz + z * sz] = src[gidx[z]];
+        }
     }
   const bool any_hn = Cfg::wc ? __any_sync(Cfg::lanes, mask != 0) : __syncthreads_or(mask != 0);
   unsigned face = 0, edge = 0, childbits = 0;
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
       mat_vec<n, T_S, false>(u, v);
       store_line<n>(A0 + bz, sz, v);
       cell_sync();
-      if (VARIANT == GV_QPOINT_CARTESIAN)
+      if (VARIANT == GV_QPOINT_CARTESIAN || ROWS)
         {
           // gradient, q-point factor w_q * h (Cartesian: J^-1 J^-T detJ = h), integrate; direction by direction
           const Number h  = valid ? static_cast<const Number *>(p.geom)[cell] : Number(0);
@@ -358,9 +378,24 @@ __global__ void __launch_bounds__(GenericCfg<n>::threads) generic_cell_kernel(co
     }
   if (valid)
     {
+      if (ROWS && row_kind > 0)
+        {
+          // distribute_local_to_global with constraints: every entry spreads over its row (transposed weights)
+          const Number *rv = static_cast<const Number *>(p.row_val);
+#pragma unroll 1
+          for (int z = 0; z < n; ++z)
+            {
+              const int i    = l + n * n * z;
+              const Number r = A0[bz + z * sz];
+              for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) atomicAdd(dst + cell_idx[p.row_col[e]], rv[e] * r);
+            }
+        }
+      else
+        {
 #pragma unroll
-      for (int z = 0; z < n; ++z)
-        if (!DIAG || l + n * n * z == unit) atomicAdd(dst + gidx[z], A0[bz + z * sz]);
+          for (int z = 0; z < n; ++z)
+            if (!DIAG || l + n * n * z == unit) atomicAdd(dst + gidx[z], A0[bz + z * sz]);
+        }
     }
   } // unit vectors
 }

@@ -19,6 +19,33 @@ struct CellLoopParams
   long long cell_begin, cell_end;
   int apply_constraints;
   int hn_mask_strategy = 0; // every warp takes the interpolation passes (MFHN_HN_MASK)
+  // GV_QPOINT_ROWS: constraint rows per distinct mask (local columns), see ConstraintRows
+  const int32_t *row_kind = nullptr; // [n_cells] 0 = unconstrained, else 1 + index of the cell's mask among the distinct masks
+  const int32_t *row_ptr  = nullptr; // [n_kinds][(k+1)^3 + 1] offsets into row_col / row_val
+  const uint16_t *row_col = nullptr; // local DoF of the cell
+  const void *row_val     = nullptr; // Number weight
+};
+
+// general-purpose constraint algorithm (MFHN_KERNEL_QPOINT_ROWS): one sparse interpolation matrix per distinct mask
+struct ConstraintRows
+{
+  int32_t *d_kind = nullptr, *d_ptr = nullptr;
+  uint16_t *d_col = nullptr;
+  void *d_val     = nullptr;
+  long long n_kinds = 0, n_entries = 0;
+  bool built = false;
+
+  void free()
+  {
+    cudaFree(d_kind);
+    cudaFree(d_ptr);
+    cudaFree(d_col);
+    cudaFree(d_val);
+    d_kind = d_ptr = nullptr;
+    d_col  = nullptr;
+    d_val  = nullptr;
+    built  = false;
+  }
 };
 
 enum GenericVariant
@@ -26,8 +53,11 @@ enum GenericVariant
   GV_QPOINT_CARTESIAN = 0, // collocation gradients, diagonal q-point factor w_q h
   GV_QPOINT_METRIC    = 1, // collocation gradients, symmetric 3x3 metric per cell
   GV_SEPARABLE        = 2, // h (K x M x M + M x K x M + M x M x K)
-  GV_QPOINT_GENERAL   = 3  // collocation gradients, symmetric 3x3 coefficient per QUADRATURE POINT
+  GV_QPOINT_GENERAL   = 3, // collocation gradients, symmetric 3x3 coefficient per QUADRATURE POINT
                            // (JxW J^-1 J^-T, [cell][6][q]): curved cells / high-order mappings
+  GV_QPOINT_ROWS      = 4  // GV_QPOINT_CARTESIAN with the GENERAL-PURPOSE constraint algorithm: hanging-node constraints
+                           // resolved entry by entry through weighted rows in the gather / scatter instead of the
+                           // interpolation passes (use_fast_hanging_node_algorithm = false, benchmark_01.h:286-293)
 };
 
 // warp-interleaved index layout of the plane kernels: [n_batches][n*n][32]

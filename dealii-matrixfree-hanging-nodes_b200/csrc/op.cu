@@ -125,6 +125,7 @@ struct Operator
   PlaneLayout plane;            // warp-interleaved layout of the plane kernels
   BulkLayout bulk;              // block descriptors of the bulk-copy kernel (degrees 3..5)
   RunsLayout runs;              // run descriptors of the run-wise bulk-copy kernel (degrees 1..5)
+  ConstraintRows rows;          // weighted constraint rows per distinct mask (general-purpose algorithm, built on first use)
   BaselineArrays baseline;      // padded deal.II-CUDA-style arrays of the baseline kernel (built on first use)
   std::vector<long long> segments;
   long long launches = 0;
@@ -149,6 +150,7 @@ struct Operator
     plane.free();
     bulk.free();
     runs.free();
+    rows.free();
   }
 };
 
@@ -178,8 +180,87 @@ void ensure_runs(Operator &op)
   runs_build(op.runs, n, op.number, op.n_cells, op.n_owned + op.n_ghost + op.vector_padding, idx.data());
 }
 
+// General-purpose constraint algorithm: one sparse interpolation matrix W per distinct mask, obtained by sending the
+// (k+1)^3 unit vectors through the interpolation kernel (double precision), stored row-wise with local column indices.
+void ensure_rows(Operator &op)
+{
+  if (op.rows.built) return;
+  const int n = op.degree + 1, n3 = n * n * n;
+  std::vector<uint8_t> masks((size_t)std::max<long long>(op.n_cells, 1), 0);
+  if (op.n_cells > 0) CUDA_CHECK(cudaMemcpy(masks.data(), op.d_masks, (size_t)op.n_cells, cudaMemcpyDeviceToHost));
+  int id_of_mask[256];
+  for (int &v : id_of_mask) v = 0;
+  std::vector<uint8_t> distinct;
+  std::vector<int32_t> kind((size_t)std::max<long long>(op.n_cells, 1), 0);
+  for (long long c = 0; c < op.n_cells; ++c)
+    if (masks[c] != 0)
+      {
+        if (id_of_mask[masks[c]] == 0)
+          {
+            distinct.push_back(masks[c]);
+            id_of_mask[masks[c]] = (int)distinct.size();
+          }
+        kind[c] = id_of_mask[masks[c]];
+      }
+  std::vector<int32_t> ptr;
+  std::vector<uint16_t> col;
+  std::vector<double> val;
+  std::vector<double> unit((size_t)n3 * n3), W((size_t)n3 * n3);
+  double *d_unit = nullptr;
+  uint8_t *d_m   = nullptr;
+  CUDA_CHECK(cudaMalloc(&d_unit, unit.size() * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&d_m, (size_t)n3));
+  for (const uint8_t m : distinct)
+    {
+      std::fill(unit.begin(), unit.end(), 0.0);
+      for (int c = 0; c < n3; ++c) unit[(size_t)c * n3 + c] = 1.0; // "cell" c holds the unit vector e_c
+      CUDA_CHECK(cudaMemcpy(d_unit, unit.data(), unit.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemset(d_m, m, (size_t)n3));
+      run_hn_only(op.degree, MFHN_F64, d_unit, d_m, n3, 0, nullptr);
+      CUDA_CHECK(cudaMemcpy(W.data(), d_unit, W.size() * sizeof(double), cudaMemcpyDeviceToHost)); // W[c][i] = (W e_c)_i
+      for (int i = 0; i < n3; ++i)
+        {
+          ptr.push_back((int32_t)col.size());
+          for (int c = 0; c < n3; ++c)
+            if (std::abs(W[(size_t)c * n3 + i]) > 1e-14)
+              {
+                col.push_back((uint16_t)c);
+                val.push_back(W[(size_t)c * n3 + i]);
+              }
+        }
+      ptr.push_back((int32_t)col.size());
+    }
+  cudaFree(d_unit);
+  cudaFree(d_m);
+  op.rows.n_kinds   = (long long)distinct.size();
+  op.rows.n_entries = (long long)col.size();
+  op.rows.d_kind    = to_device(kind);
+  op.rows.d_ptr     = to_device(ptr);
+  op.rows.d_col     = to_device(col);
+  if (op.number == MFHN_F64)
+    op.rows.d_val = to_device(val);
+  else
+    {
+      std::vector<float> vf(val.begin(), val.end());
+      op.rows.d_val = to_device(vf);
+    }
+  op.rows.built = true;
+}
+
 void launch_kernel(Operator &op, int kernel, const CellLoopParams &p, cudaStream_t stream)
 {
+  if (kernel == MFHN_KERNEL_QPOINT_ROWS)
+    {
+      ensure_rows(op);
+      CellLoopParams q = p;
+      q.row_kind       = op.rows.d_kind;
+      q.row_ptr        = op.rows.d_ptr;
+      q.row_col        = op.rows.d_col;
+      q.row_val        = op.rows.d_val;
+      run_generic(op.degree, op.number, GV_QPOINT_ROWS, false, q, op.device, stream);
+      ++op.launches;
+      return;
+    }
   if (kernel == MFHN_KERNEL_BASELINE)
     {
       run_baseline(op.degree, op.number, op.baseline, op.d_idx, op.d_geom, op.n_cells, p, op.device, stream);
@@ -261,7 +342,7 @@ int resolve_kernel(const Operator &op)
       if (kernel == MFHN_KERNEL_PLANE && op.degree == 3 && op.number == MFHN_F32) kernel = MFHN_KERNEL_RUNS;
       if (kernel == MFHN_KERNEL_PLANE && op.degree == 5 && op.bulk.usable) kernel = MFHN_KERNEL_BULK;
     }
-  if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT)
+  if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT && kernel != MFHN_KERNEL_QPOINT_ROWS)
     throw InvalidArgument("affine / general geometry requires MFHN_KERNEL_QPOINT");
   if (kernel == MFHN_KERNEL_BULK && !bulk_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_BULK is available for degrees 3..5");
   if (kernel == MFHN_KERNEL_BULK && op.geometry_type == MFHN_GEOM_CARTESIAN && !op.bulk.usable)
@@ -269,7 +350,8 @@ int resolve_kernel(const Operator &op)
   if (kernel == MFHN_KERNEL_RUNS && !runs_supported(op.degree + 1)) throw NotImplemented("MFHN_KERNEL_RUNS is available for degrees 1..5");
   if (kernel == MFHN_KERNEL_PATCH)
     throw NotImplemented("MFHN_KERNEL_PATCH (sorted-unique patch gather, round 1) was measured slower than the plane kernel and has been removed");
-  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_RUNS || kernel == MFHN_KERNEL_SEPARABLE) && op.geometry_type != MFHN_GEOM_CARTESIAN)
+  if ((kernel == MFHN_KERNEL_PLANE || kernel == MFHN_KERNEL_BULK || kernel == MFHN_KERNEL_RUNS || kernel == MFHN_KERNEL_SEPARABLE ||
+       kernel == MFHN_KERNEL_QPOINT_ROWS) && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("this kernel requires Cartesian geometry");
   if (kernel == MFHN_KERNEL_BASELINE && op.geometry_type != MFHN_GEOM_CARTESIAN)
     throw InvalidArgument("the baseline kernel is set up for Cartesian cells");
@@ -308,7 +390,7 @@ Operator *op_create(const mfhn_op_desc &d)
   if (d.n_cells > 0 && (!d.dof_indices || !d.masks || !d.geometry)) throw InvalidArgument("null array");
   if (d.geometry_type != MFHN_GEOM_CARTESIAN && d.geometry_type != MFHN_GEOM_AFFINE && d.geometry_type != MFHN_GEOM_GENERAL)
     throw InvalidArgument("unknown geometry type");
-  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_RUNS) throw InvalidArgument("unknown kernel");
+  if (d.kernel < MFHN_KERNEL_AUTO || d.kernel > MFHN_KERNEL_QPOINT_ROWS) throw InvalidArgument("unknown kernel");
   int device = d.device;
   if (device < 0)
     CUDA_CHECK(cudaGetDevice(&device));
@@ -711,7 +793,7 @@ int mfhn_op_set_kernel(mfhn_op h, int kernel)
     if (!h) throw InvalidArgument("null argument");
     Operator &op  = *reinterpret_cast<Operator *>(h);
     const int old = op.kernel;
-    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_RUNS) throw InvalidArgument("unknown kernel");
+    if (kernel < MFHN_KERNEL_AUTO || kernel > MFHN_KERNEL_QPOINT_ROWS) throw InvalidArgument("unknown kernel");
     op.kernel = kernel;
     try
       {
@@ -787,6 +869,11 @@ int mfhn_op_query(mfhn_op h, const char *what, double *value)
       }
     else if (w == "runs_staging_wavefronts") // bank model of the staging reads (MFHN_RUNS_STATS=1 at creation), 2 per plane slot and batch = no conflict
       *value = (double)op.runs.staging_wavefronts;
+    else if (w == "constraint_row_entries") // general-purpose constraint algorithm: non-zeros of the interpolation matrices of all distinct masks
+      {
+        ensure_rows(op);
+        *value = (double)op.rows.n_entries;
+      }
     else if (w == "bulk_irregular_cells") // cells the bulk-copy kernel leaves to the plane kernel (-1: layout not usable)
       *value = op.bulk.usable ? (double)op.bulk.irregular.size() : -1.0;
     else

@@ -57,6 +57,10 @@ typedef struct mfhn_op_s *mfhn_op;
 #define MFHN_KERNEL_RUNS 7      /* plane kernel; every cell's vector entries cut into contiguous runs at setup (any
                                    numbering), long runs moved by the bulk-copy engine, the rest entry by entry;
                                    degrees 1..5, 16-byte aligned vectors */
+#define MFHN_KERNEL_QPOINT_ROWS 8 /* QPOINT on Cartesian cells with the GENERAL-PURPOSE constraint algorithm: hanging-node
+                                   constraints resolved entry by entry through weighted rows in the gather / scatter, no
+                                   interpolation passes (use_fast_hanging_node_algorithm = false, benchmark_01.h:286-293;
+                                   t6 / t7 of benchmark_01.cc:222-234) */
 
 const char *mfhn_last_error(void);
 const char *mfhn_version(void);

@@ -534,6 +534,19 @@ def test_hn_mask_strategy_and_dg_copy(mfhn, k):
             op.set_hn_strategy("branch")
         y = dst.cpu().numpy()
         assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12, (k, kern)
+    # general-purpose constraint algorithm (use_fast_hanging_node_algorithm = false, benchmark_01.h:286-293): weighted
+    # constraint rows in the gather / scatter instead of the interpolation passes -- same operator
+    for number in ("double", "float"):
+        opr = mfhn.LaplaceOperator(mf, number=number, kernel="qpoint_rows")
+        s2, d2 = opr.initialize_dof_vector(), opr.initialize_dof_vector()
+        s2.copy_(torch.from_numpy(x).to(s2.dtype))
+        opr.vmult(d2, s2)
+        assert np.abs(d2.double().cpu().numpy() - ref).max() / np.abs(ref).max() < TOL[number], (k, number)
+        assert opr.query("constraint_row_entries") > (k + 1) ** 3
+        opr.set_apply_constraints(False)
+        opr.vmult(d2, s2, zero_dst=True)
+        ref_nc = operators.vmult_fast(lay, x, apply_constraints=False)
+        assert np.abs(d2.double().cpu().numpy() - ref_nc).max() / np.abs(ref_nc).max() < TOL[number]
     # DG (C): cell-local values, constraints on / off
     n, n3 = k + 1, (k + 1) ** 3
     rng = np.random.default_rng(3)
