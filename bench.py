@@ -538,8 +538,10 @@ def run():
         torch.cuda.empty_cache()
         out["stages"] = stage_benchmarks(mfhn, torch, args, L, time_vmult)
 
+    force = False
     extras = not args.no_extras and not args.minimal and args.refinements is None and args.mapping == "cartesian" and args.degree == 4 and not args.stages
-    if extras and world in (1, 8):
+    force = bool(os.environ.get("MFHN_BENCH_FORCE_EXTRAS"))  # development: the 8-GPU extras at any N > 1
+    if extras and (world in (1, 8) or force):
         # BASELINE.json config 5: CG + point-Jacobi at degree 6 (N=1: annulus L=8, N=8: annulus L=9, 477 M DoFs)
         import copy
 
@@ -561,7 +563,7 @@ def run():
         log("high-order extra")
         out["high_order_mapping"] = high_order_benchmark(mfhn, torch, args, time_vmult, peaks()[0])
 
-    if world == 8 and not args.no_weak and not args.minimal and args.refinements is None:
+    if (world == 8 or (force and world > 1)) and not args.no_weak and not args.minimal and args.refinements is None:
         # weak scaling (BASELINE.json config 4): the next finer mesh on 8 GPUs (annulus L=10, k=4: 1.124 B DoFs, 140.5 M per GPU).
         # Not comparable with the N=1 line DoF for DoF: the finer mesh has half the share of cells with hanging nodes, so
         # its efficiency is quoted against this run's own rank-local cell loops.
