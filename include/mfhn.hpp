@@ -242,6 +242,32 @@ public:
     check(mfhn_op_query(op_, what, &v));
     return v;
   }
+  // switches of the reference's stage decomposition (benchmark_01.cc:70-116, 179-234)
+  void set_apply_constraints(const bool flag) { check(mfhn_op_set_apply_constraints(op_, flag)); } // do_apply_constraints
+  void set_kernel(const int kernel) { check(mfhn_op_set_kernel(op_, kernel)); }                   // e.g. MFHN_KERNEL_QPOINT_ROWS: general-purpose algorithm
+  void set_hn_strategy(const int strategy) { check(mfhn_op_set_hn_strategy(op_, strategy)); }     // MFHN_HN_BRANCH / MFHN_HN_MASK
+  // "DG (C)": dst_cells += [W^T W] src_cells on cell-local arrays [n_cells][(fe_degree+1)^3] (device pointers)
+  void dg_copy(Number *dst_cells, const Number *src_cells, cudaStream_t stream = nullptr) const { check(mfhn_op_dg_copy(op_, dst_cells, src_cells, stream)); }
+
+  // Extension (BASELINE.json config 5; the reference has no solver): 1 / diag(A), and CG with point-Jacobi -- one
+  // (partitioned) vmult, two fused vector kernels and one batched all-reduce per iteration, all inside the library
+  void compute_inverse_diagonal(VectorType &inv_diag, cudaStream_t stream = nullptr) const
+  {
+    initialize_dof_vector(inv_diag);
+    check(mfhn_op_inverse_diagonal(op_, dist_, inv_diag.data(), stream));
+  }
+  mfhn_cg_result solve_cg(VectorType &x, const VectorType &b, const VectorType *inv_diag, const double rel_tol = 1e-8, const int max_iter = 1000,
+                          const bool timings = false, cudaStream_t stream = nullptr) const
+  {
+    mfhn_cg_options opt{};
+    opt.max_iter    = max_iter;
+    opt.rel_tol     = rel_tol;
+    opt.check_every = 10;
+    opt.timings     = timings;
+    mfhn_cg_result res{};
+    check(mfhn_cg_solve(op_, dist_, x.data(), b.data(), inv_diag ? inv_diag->data() : nullptr, &opt, &res, nullptr, stream));
+    return res;
+  }
 
 private:
   const MatrixFree &matrix_free_;
