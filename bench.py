@@ -126,14 +126,14 @@ class ClockSampler:
 
 
 def default_refinements(args):
-    """The same mesh at every N (strong scaling): SURVEY 8d / BASELINE.md C2: annulus (p4est flavour) L=9 for k <= 4
-    (142.8 M DoFs at k=4), L=8 for k >= 5.  The 8-GPU weak-scaling run on L+1 is an extra key of the N=8 line."""
+    """The same mesh at every N (strong scaling) and every degree: annulus (p4est flavour) L=9 (142.8 M DoFs at k=4;
+    SURVEY 8d / BASELINE.md C2).  The 8-GPU weak-scaling run on L+1 is an extra key of the N=8 line."""
     if args.refinements is not None:
         return args.refinements
     if args.mapping == "high-order":
         return 8 if args.degree <= 4 else 7  # 6 s (k+1)^3 bytes of coefficients per cell: 1.6 GB at L=8, k=4
     if args.geometry == "annulus":
-        return 9 if args.degree <= 4 else 8
+        return 9  # every degree on the same mesh: 142.8 M DoFs at k=4, 477 M at k=6, 1.12 B at k=8
     return 8 if args.degree <= 4 else 7
 
 
@@ -542,7 +542,7 @@ def run():
     extras = not args.no_extras and not args.minimal and args.refinements is None and args.mapping == "cartesian" and args.degree == 4 and not args.stages
     force = bool(os.environ.get("MFHN_BENCH_FORCE_EXTRAS"))  # development: the 8-GPU extras at any N > 1
     if extras and (world in (1, 8) or force):
-        # BASELINE.json config 5: CG + point-Jacobi at degree 6 (N=1: annulus L=8, N=8: annulus L=9, 477 M DoFs)
+        # BASELINE.json config 5: CG + point-Jacobi at degree 6 on the same mesh (annulus L=9, 477 M DoFs)
         import copy
 
         from bench_dist import cg_benchmark
@@ -551,7 +551,7 @@ def run():
         a2.degree, a2.cg_iterations = 6, 60
         log("cg extra")
         extras_keep = []
-        res = cg_benchmark(mfhn, torch, dist if world > 1 else None, a2, 8 if world == 1 else 9, rank, world, keep=extras_keep)
+        res = cg_benchmark(mfhn, torch, dist if world > 1 else None, a2, 9, rank, world, keep=extras_keep)
         out["cg_jacobi"] = {k: res[k] for k in ("value", "unit", "iterations", "residual_reduction", "ms_per_iteration", "gdofs_per_iteration",
                                                 "vector_kernels_gbs", "config")}
         if world == 1:

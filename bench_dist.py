@@ -55,11 +55,12 @@ def build_problem(mfhn, args, L, rank, world):
 def degree_sweep(mfhn, torch, args, time_vmult, hbm_peak, full=False):
     """BASELINE.json metric "per degree 1-8" (configs 2 and 3): every degree on the annulus mesh in double and float,
     with and without constraints, through the kernel AUTO picks; frac = accumulating-vmult bytes / time / HBM peak.
-    L = 9 for k <= 4 and 8 above; full=True adds L = 10 for k = 1, 2 (the L = 9 problems have 2.3 M / 18 M
-    DoFs only) and the other kernels."""
+    Every degree runs on the headline mesh (L = 9: 2.3 M DoFs at k = 1 ... 1.12 B at k = 8; the L = 8 mesh SURVEY 8d
+    suggests for k >= 5 has twice the share of constrained cells and too few cells to fill the GPU: k = 5 reads 120 GDoF/s /
+    20 % overhead there and 135 / 6 % here); full=True adds L = 10 for k = 1, 2 and the other kernels."""
     res = []
     for k in range(1, 9):
-        base = (9 if k <= 4 else 8) if args.refinements is None else max(args.refinements - (0 if k <= 4 else 1), 2)
+        base = 9 if args.refinements is None else max(args.refinements - (0 if k <= 4 else 1), 2)
         for L in ([base, base + 1] if (full and k <= 2) else [base]):
             tria = mfhn.Triangulation(args.geometry, L, "p4est")
             dh = mfhn.DoFHandler(tria, k)
