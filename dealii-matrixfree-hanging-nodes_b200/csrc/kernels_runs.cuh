@@ -335,7 +335,7 @@ void launch_runs_impl(const RunsLayout &L, const CellLoopParams &cp, int device,
   if (nb <= 0) return;
   const unsigned grid = (unsigned)((nb + R::warps - 1) / R::warps);
   constexpr bool reg_bound = sizeof(Number) == 8 && n >= 5;
-  const int occ = occupancy_choice(n, sizeof(Number) == 8, 5); // measured on B200 (k = 4: 5 CTAs 120.4, 6 CTAs 109.6-114.7 GDoF/s)
+  const int occ = occupancy_choice(n, sizeof(Number) == 8, n == 5 ? 5 : 4); // measured on B200 (k = 4: 5 CTAs 120.4, 6 CTAs 109.6-114.7; k = 5: 4 CTAs 138.2, 5 CTAs 98.5 GDoF/s)
   if (reg_bound && occ == 5)
     launch_runs_occ<n, Number, reg_bound ? 5 : 4>(p, grid, device, stream);
   else if (reg_bound && occ == 6)

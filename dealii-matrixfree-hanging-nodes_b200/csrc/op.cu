@@ -340,6 +340,8 @@ int resolve_kernel(const Operator &op)
       //   k=5: plane 93.6 | 139.2, bulk 120.1 | 141.1, runs 113.2 | 124.6;  k=1,2: plane ahead of runs by 20-50 %
       if (kernel == MFHN_KERNEL_PLANE && op.degree == 4) kernel = MFHN_KERNEL_RUNS;
       if (kernel == MFHN_KERNEL_PLANE && op.degree == 3 && op.number == MFHN_F32) kernel = MFHN_KERNEL_RUNS;
+      //   k=5 on the L=9 mesh (profiles/r2_kernel_choice_k5_L9.jsonl): runs 138.2 (4 CTAs), bulk 135.6
+      if (kernel == MFHN_KERNEL_PLANE && op.degree == 5 && op.number == MFHN_F64) kernel = MFHN_KERNEL_RUNS;
       if (kernel == MFHN_KERNEL_PLANE && op.degree == 5 && op.bulk.usable) kernel = MFHN_KERNEL_BULK;
     }
   if (op.geometry_type != MFHN_GEOM_CARTESIAN && kernel != MFHN_KERNEL_QPOINT && kernel != MFHN_KERNEL_QPOINT_ROWS)
