@@ -309,7 +309,9 @@ int64_t mfhn_dist_launch_count(mfhn_dist d);
  * peer-mapped (CUDA IPC) pointers over NVLink -- no pack / unpack kernels, no data-path collective;
  * two 4-byte all-reduces act as barriers.  The vector pair must come from mfhn_vec_alloc so that it
  * can be exported; every rank passes the opened peer pointers of all ranks.  The boundary cells run
- * through the plane kernels (all degrees), the interior cells through the operator's own kernel. */
+ * through the plane kernels (all degrees), the interior cells through the operator's own kernel.
+ * mfhn_vec_alloc returns zeroed memory in whole 2 MiB blocks: a CUDA IPC handle maps the allocation BLOCK, so a
+ * vector that shared a block with other small allocations would be opened at the wrong address by its peers. */
 int mfhn_vec_alloc(int64_t bytes, void **dev_ptr);
 int mfhn_vec_free(void *dev_ptr);
 int mfhn_ipc_get_handle(void *dev_ptr, void *handle64);
